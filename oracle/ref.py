@@ -1,0 +1,136 @@
+"""TEST INFRASTRUCTURE -- ctypes view of oracle/_ref/libnq_ref.so.
+
+That library is the UNMODIFIED reference (dafx/libnyquist, bundled Opus float
+build) compiled in place by oracle/Makefile; see oracle/ref_harness.c for the
+reference file:line each entry wraps.  Only tests/, __graft_entry__.smoke()
+and bench.py (cpu_baseline leg, --impl reference) may import this module; the
+product package libnyquist_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "libnq_ref.so")
+
+FRAME = 960
+HALF_OVL = 60
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(LIB_PATH)
+        fp = C.POINTER(C.c_float)
+        L.nqref_opus_ifft.argtypes = [C.c_int, fp, fp]
+        L.nqref_clt_mdct_backward.argtypes = [fp, fp, C.c_int, C.c_int]
+        L.nqref_compute_inv_mdcts.argtypes = [C.c_int, fp, C.POINTER(fp), C.c_int, C.c_int]
+        L.nqref_synth_batch.argtypes = [fp, C.c_void_p, fp, fp, fp, C.c_long, C.c_int]
+        L.nqref_synth_batch_mt.argtypes = [fp, C.c_void_p, fp, fp, fp, C.c_long, C.c_int, C.c_int]
+        L.nqref_synth_batch_mt.restype = C.c_double
+        L.nqref_decode_memory.argtypes = [C.c_void_p, C.c_size_t, fp, C.c_long, C.POINTER(C.c_int), C.c_int]
+        L.nqref_decode_memory.restype = C.c_long
+        L.nqref_record_count.restype = C.c_long
+        L.nqref_record_floats.restype = C.c_size_t
+        L.nqref_record_copy.argtypes = [fp]
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def tables():
+    """The reference's static tables (static_modes_float.h:9,99,343-417,477)."""
+    L = lib()
+    out = dict(
+        window120=np.zeros(120, np.float32),
+        trig481=np.zeros(481, np.float32),
+        twiddles480=np.zeros(960, np.float32),
+        bitrev480=np.zeros(480, np.int16),
+        bitrev240=np.zeros(240, np.int16),
+        bitrev120=np.zeros(120, np.int16),
+        bitrev60=np.zeros(60, np.int16),
+    )
+    L.nqref_tables(*[v.ctypes.data_as(C.c_void_p) for v in out.values()])
+    return out
+
+
+def opus_ifft(x_ri: np.ndarray, shift: int) -> np.ndarray:
+    """kiss_fft.c:696 with the static state mode->mdct.kfft[shift]; interleaved re/im."""
+    x = np.ascontiguousarray(x_ri, np.float32)
+    assert x.size == 2 * (480 >> shift)
+    y = np.zeros_like(x)
+    lib().nqref_opus_ifft(shift, _fp(x), _fp(y))
+    return y
+
+
+def clt_mdct_backward(inp: np.ndarray, out: np.ndarray, shift: int, stride: int) -> None:
+    """mdct.c:267.  `out` (>= N2+60 floats) is read-modify-written in place."""
+    assert inp.dtype == np.float32 and out.dtype == np.float32
+    assert inp.flags.c_contiguous and out.flags.c_contiguous
+    lib().nqref_clt_mdct_backward(_fp(inp), _fp(out), shift, stride)
+
+
+def synth_batch(coef, transient, tail_in=None, nthreads=1):
+    """compute_inv_mdcts (celt_decoder_clean.c:264) over a batch of LM=3 frames.
+
+    coef [nframes][C][960] f32, transient [nframes] u8, tail_in [C][60] or None.
+    Returns (pcm [nframes*960][C], tail_out [C][60], seconds).
+    """
+    coef = np.ascontiguousarray(coef, np.float32)
+    nframes, Cn, n = coef.shape
+    assert n == FRAME
+    tr = np.ascontiguousarray(transient, np.uint8)
+    assert tr.shape == (nframes,)
+    ti = None if tail_in is None else np.ascontiguousarray(tail_in, np.float32)
+    pcm = np.zeros((nframes * FRAME, Cn), np.float32)
+    tail = np.zeros((Cn, HALF_OVL), np.float32)
+    sec = lib().nqref_synth_batch_mt(_fp(coef), tr.ctypes.data_as(C.c_void_p), _fp(ti),
+                                     _fp(pcm), _fp(tail), nframes, Cn, int(nthreads))
+    return pcm, tail, sec
+
+
+def decode_file(path: str, record: bool = False):
+    """Whole-file decode through opusfile, as src/OpusDecoder.cpp:57-119 does.
+
+    Returns (pcm [nsamples][channels] f32, records or None).  Each record is
+    a dict(nch, shift, B, coef [nch][n], out [nch][n]) captured at the
+    inverse-MDCT call sites (celt_decoder_clean.c:290,298,309).
+    """
+    L = lib()
+    data = np.fromfile(path, np.uint8)
+    ch = C.c_int(0)
+    n = L.nqref_decode_memory(data.ctypes.data_as(C.c_void_p), data.size, None, 0, C.byref(ch), 0)
+    if n < 0:
+        raise RuntimeError(f"reference could not decode {path}: {n}")
+    pcm = np.zeros((n, ch.value), np.float32)
+    n2 = L.nqref_decode_memory(data.ctypes.data_as(C.c_void_p), data.size, _fp(pcm), pcm.size,
+                               C.byref(ch), 1 if record else 0)
+    assert n2 == n
+    recs = None
+    if record:
+        flat = np.zeros(L.nqref_record_floats(), np.float32)
+        L.nqref_record_copy(_fp(flat))
+        L.nqref_record_free()
+        recs = []
+        p = 0
+        while p < flat.size:
+            nch, shift, B, nn = flat[p:p + 4].view(np.int32)
+            p += 4
+            coef = flat[p:p + nch * nn].reshape(nch, nn); p += nch * nn
+            out = flat[p:p + nch * nn].reshape(nch, nn); p += nch * nn
+            recs.append(dict(nch=int(nch), shift=int(shift), B=int(B), coef=coef, out=out))
+    return pcm, recs

@@ -1,0 +1,279 @@
+/* TEST INFRASTRUCTURE -- builds oracle/_ref/libnq_ref.so, the UNMODIFIED
+ * reference compiled in place from /root/reference (see oracle/Makefile).
+ *
+ * Nothing of the reference is copied: this file unity-includes the
+ * reference's own translation unit (src/OpusDependencies.c, which itself
+ * #includes every CELT/SILK/opusfile/ogg .c file, lines 78-270) and adds thin
+ * exported wrappers so Python tests / bench.py's cpu_baseline and reference
+ * arm can call the reference functions on arbitrary buffers:
+ *
+ *   opus_ifft            third_party/opus/celt/kiss_fft.c:696
+ *   clt_mdct_backward    third_party/opus/celt/mdct.c:267
+ *   compute_inv_mdcts    third_party/opus/celt/celt_decoder_clean.c:264 (static)
+ *   whole-file decode    opusfile op_open_memory / op_read_float
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg and
+ * --impl reference) may load the resulting library.  The product
+ * (libnyquist_b200/) never does.
+ */
+#include "OpusDependencies.c"
+
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define NQREF_API __attribute__((visibility("default")))
+
+#define FRAME 960   /* samples per channel per 20 ms frame (LM = 3)        */
+#define OVL 120     /* mode->overlap                                        */
+#define HALF_OVL 60 /* raw tail carried between consecutive (sub-)blocks   */
+
+static const CELTMode *the_mode(void)
+{
+    return opus_custom_mode_create(48000, 960, NULL);
+}
+
+/* ---- static tables (static_modes_float.h:9,99,343..417,477) ------------- */
+NQREF_API void nqref_tables(float *window120, float *trig481, float *twiddles480_ri,
+                            int16_t *bitrev480, int16_t *bitrev240,
+                            int16_t *bitrev120, int16_t *bitrev60)
+{
+    const CELTMode *m = the_mode();
+    int i;
+    for (i = 0; i < 120; i++) window120[i] = m->window[i];
+    for (i = 0; i <= 480; i++) trig481[i] = m->mdct.trig[i];
+    for (i = 0; i < 480; i++) {
+        twiddles480_ri[2 * i] = m->mdct.kfft[0]->twiddles[i].r;
+        twiddles480_ri[2 * i + 1] = m->mdct.kfft[0]->twiddles[i].i;
+    }
+    for (i = 0; i < 480; i++) bitrev480[i] = m->mdct.kfft[0]->bitrev[i];
+    for (i = 0; i < 240; i++) bitrev240[i] = m->mdct.kfft[1]->bitrev[i];
+    for (i = 0; i < 120; i++) bitrev120[i] = m->mdct.kfft[2]->bitrev[i];
+    for (i = 0; i < 60; i++) bitrev60[i] = m->mdct.kfft[3]->bitrev[i];
+}
+
+/* ---- a3.2: opus_ifft with the static state kfft[shift] ------------------ */
+NQREF_API void nqref_opus_ifft(int shift, const float *in_ri, float *out_ri)
+{
+    const CELTMode *m = the_mode();
+    opus_ifft(m->mdct.kfft[shift], (const kiss_fft_cpx *)in_ri, (kiss_fft_cpx *)out_ri);
+}
+
+/* ---- a3: one clt_mdct_backward call (out is read-modify-write) ---------- */
+NQREF_API void nqref_clt_mdct_backward(float *in, float *out, int shift, int stride)
+{
+    const CELTMode *m = the_mode();
+    clt_mdct_backward(&m->mdct, in, out, m->window, OVL, shift, stride);
+}
+
+/* ---- a1: compute_inv_mdcts on caller buffers ---------------------------- */
+NQREF_API void nqref_compute_inv_mdcts(int shortBlocks, float *X, float **out_mem,
+                                       int C, int LM)
+{
+    compute_inv_mdcts(the_mode(), shortBlocks, X, out_mem, C, LM);
+}
+
+/* ---- batch driver: the frame loop of celt_decode_with_ec reduced to the
+ *      synthesis stage (history shift :622-626, out_syn :638-642, call :656).
+ *      coef      [nframes][C][960]
+ *      transient [nframes]           (non-zero => shortBlocks = 8)
+ *      tail_in   [C][60] or NULL     (raw tail of the frame before the batch)
+ *      pcm_out   [nframes*960][C]    interleaved celt_sig (pre post-filter)
+ *      tail_out  [C][60] or NULL
+ */
+static void synth_range(const float *coef, const uint8_t *transient,
+                        const float *tail_in, float *pcm_out, float *tail_out,
+                        long f0, long f1, int C, int warm)
+{
+    const CELTMode *m = the_mode();
+    float *mem = (float *)calloc((size_t)C * (FRAME + HALF_OVL), sizeof(float));
+    float *X = (float *)malloc((size_t)C * FRAME * sizeof(float));
+    float **out_syn = (float **)malloc((size_t)C * sizeof(float *));
+    long f;
+    int c, i;
+    for (c = 0; c < C; c++) {
+        out_syn[c] = mem + (size_t)c * (FRAME + HALF_OVL);
+        if (tail_in)
+            memcpy(out_syn[c] + FRAME, tail_in + c * HALF_OVL, HALF_OVL * sizeof(float));
+    }
+    /* warm: recompute frame f0-1 only to obtain its raw tail (shard halo) */
+    for (f = warm ? f0 - 1 : f0; f < f1; f++) {
+        for (c = 0; c < C; c++) /* what OPUS_MOVE at :625 does to the tail */
+            memmove(out_syn[c], out_syn[c] + FRAME, HALF_OVL * sizeof(float));
+        memcpy(X, coef + (size_t)f * C * FRAME, (size_t)C * FRAME * sizeof(float));
+        compute_inv_mdcts(m, transient[f] ? 8 : 0, X, out_syn, C, 3);
+        if (f < f0) continue;
+        if (pcm_out)
+            for (c = 0; c < C; c++)
+                for (i = 0; i < FRAME; i++)
+                    pcm_out[((size_t)f * FRAME + i) * C + c] = out_syn[c][i];
+    }
+    if (tail_out)
+        for (c = 0; c < C; c++)
+            memcpy(tail_out + c * HALF_OVL, out_syn[c] + FRAME, HALF_OVL * sizeof(float));
+    free(out_syn);
+    free(X);
+    free(mem);
+}
+
+NQREF_API void nqref_synth_batch(const float *coef, const uint8_t *transient,
+                                 const float *tail_in, float *pcm_out, float *tail_out,
+                                 long nframes, int C)
+{
+    synth_range(coef, transient, tail_in, pcm_out, tail_out, 0, nframes, C, 0);
+}
+
+typedef struct {
+    const float *coef; const uint8_t *transient; const float *tail_in;
+    float *pcm_out; float *tail_out; long f0, f1; int C; int warm;
+} range_job;
+
+static void *range_thread(void *p)
+{
+    range_job *j = (range_job *)p;
+    synth_range(j->coef, j->transient, j->tail_in, j->pcm_out, j->tail_out,
+                j->f0, j->f1, j->C, j->warm);
+    return NULL;
+}
+
+/* Same result as nqref_synth_batch, contiguous frame ranges on nthreads host
+ * threads; a range that does not start at 0 recomputes the previous frame
+ * for its tail.  Returns the wall time in seconds of the threaded region. */
+NQREF_API double nqref_synth_batch_mt(const float *coef, const uint8_t *transient,
+                                      const float *tail_in, float *pcm_out, float *tail_out,
+                                      long nframes, int C, int nthreads)
+{
+    pthread_t *th;
+    range_job *jobs;
+    struct timespec t0, t1;
+    int t;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > nframes) nthreads = nframes > 0 ? (int)nframes : 1;
+    th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    jobs = (range_job *)malloc(sizeof(range_job) * nthreads);
+    the_mode();
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (t = 0; t < nthreads; t++) {
+        range_job *j = &jobs[t];
+        j->coef = coef; j->transient = transient; j->pcm_out = pcm_out; j->C = C;
+        j->f0 = nframes * t / nthreads;
+        j->f1 = nframes * (t + 1) / nthreads;
+        j->warm = j->f0 > 0;
+        j->tail_in = j->f0 == 0 ? tail_in : NULL;
+        j->tail_out = t == nthreads - 1 ? tail_out : NULL;
+        pthread_create(&th[t], NULL, range_thread, j);
+    }
+    for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(jobs);
+    free(th);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ---- whole-file decode with taps on the inverse-MDCT call sites ----------
+ * The overlay oracle/ref_overlay/opus/celt/celt_decoder_clean.c routes the
+ * calls at celt_decoder_clean.c:290,298,309 through these taps.  When a
+ * recording is active each tap appends one record:
+ *   header  int32[4] = {nch_in_call, shift, stride(B), N2*B}
+ *   coef    nch * N2*B floats  (the frame's freq[] for these channels, as
+ *                               handed to compute_inv_mdcts)
+ *   out     nch * N2*B floats  (out_syn after the last sub-block, i.e. the
+ *                               synthesis output before comb_filter)
+ */
+typedef struct {
+    int active;
+    float *buf; size_t len, cap;   /* in floats */
+    long nrecords;
+    int b;                         /* sub-block counter inside a stride-B group */
+    float *xbase[2], *obase[2];
+} recorder;
+static recorder g_rec;
+
+static void rec_reserve(size_t extra)
+{
+    if (g_rec.len + extra > g_rec.cap) {
+        size_t ncap = g_rec.cap ? g_rec.cap * 2 : (1u << 20);
+        while (ncap < g_rec.len + extra) ncap *= 2;
+        g_rec.buf = (float *)realloc(g_rec.buf, ncap * sizeof(float));
+        g_rec.cap = ncap;
+    }
+}
+
+static void rec_group(int nch, int shift, int B, float **in, float **out)
+{
+    int N2 = (1920 >> shift) >> 1, c;
+    if (g_rec.b == 0)
+        for (c = 0; c < nch; c++) { g_rec.xbase[c] = in[c]; g_rec.obase[c] = out[c]; }
+    if (++g_rec.b < B) return;
+    g_rec.b = 0;
+    {
+        int32_t hdr[4] = {nch, shift, B, N2 * B};
+        size_t n = (size_t)N2 * B;
+        rec_reserve(4 + 2 * nch * n);
+        memcpy(g_rec.buf + g_rec.len, hdr, sizeof hdr); g_rec.len += 4;
+        for (c = 0; c < nch; c++) { memcpy(g_rec.buf + g_rec.len, g_rec.xbase[c], n * 4); g_rec.len += n; }
+        for (c = 0; c < nch; c++) { memcpy(g_rec.buf + g_rec.len, g_rec.obase[c], n * 4); g_rec.len += n; }
+        g_rec.nrecords++;
+    }
+}
+
+void nqref_tap_mdct_b1c2(const mdct_lookup *l, float *in[2], float *out[2],
+                         const float *window, int overlap, int shift, int stride)
+{
+    clt_mdct_backward_B1_C2(l, in, out, window, overlap, shift, stride);
+    if (g_rec.active) rec_group(2, shift, stride, in, out);
+}
+
+void nqref_tap_mdct(const mdct_lookup *l, float *in, float *out,
+                    const float *window, int overlap, int shift, int stride)
+{
+    clt_mdct_backward(l, in, out, window, overlap, shift, stride);
+    if (g_rec.active) rec_group(1, shift, stride, &in, &out);
+}
+
+/* Decode an in-memory Ogg Opus file the way src/OpusDecoder.cpp:57-119 does
+ * (op_test_memory/op_test_open/op_read_float loop).  Returns samples per
+ * channel decoded (<0 on error).  pcm may be NULL (count only).  If record
+ * != 0 the taps above log every synthesis call; fetch with nqref_record_*. */
+NQREF_API long nqref_decode_memory(const unsigned char *data, size_t nbytes,
+                                   float *pcm, long pcm_capacity_floats,
+                                   int *channels_out, int record)
+{
+    int err = 0, ch;
+    long total = 0;
+    float scratch[5760 * 8];
+    OggOpusFile *of = op_test_memory(data, nbytes, &err);
+    if (!of) return -1;
+    if (op_test_open(of) != 0) return -2;   /* frees of on failure */
+    ch = op_head(of, 0)->channel_count;
+    if (channels_out) *channels_out = ch;
+    g_rec.active = record; g_rec.len = 0; g_rec.nrecords = 0; g_rec.b = 0;
+    for (;;) {
+        float *dst = scratch;
+        int room = (int)(sizeof scratch / sizeof scratch[0]);
+        int got;
+        if (pcm) {
+            long left = pcm_capacity_floats - total * ch;
+            if (left <= 0) break;
+            dst = pcm + total * ch;
+            room = left > (1 << 30) ? (1 << 30) : (int)left;
+        }
+        got = op_read_float(of, dst, room, NULL);
+        if (got == 0) break;
+        if (got < 0) { total = got; break; }
+        total += got;
+    }
+    g_rec.active = 0;
+    op_free(of);
+    return total;
+}
+
+NQREF_API long nqref_record_count(void) { return g_rec.nrecords; }
+NQREF_API size_t nqref_record_floats(void) { return g_rec.len; }
+NQREF_API void nqref_record_copy(float *dst) { memcpy(dst, g_rec.buf, g_rec.len * sizeof(float)); }
+NQREF_API void nqref_record_free(void)
+{
+    free(g_rec.buf); g_rec.buf = NULL; g_rec.len = g_rec.cap = 0; g_rec.nrecords = 0;
+}

@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz|*.bin from the reference.  Runs ONLY where
+/root/reference exists (this container); the GPU box uses the committed files.
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Outputs (all small):
+  ifft_{input,output}_N{480,60}.bin  byte copies of the reference's own golden
+                                     vectors (test_data/)
+  ref_tables.npz     the reference's static tables (static_modes_float.h)
+  synth_cases.npz    compute_inv_mdcts outputs of the COMPILED REFERENCE on
+                     seeded synthetic batches: long / short / mixed, mono /
+                     stereo / 3ch / 8ch, zero and non-zero initial tail
+  mdct_calls.npz     single clt_mdct_backward calls for every (shift, stride)
+  real_frames.npz    runs of consecutive frames recorded at the inverse-MDCT
+                     call sites while the reference decodes the bundled
+                     sb-reverie.opus / sb-reverie-60ms-frames.opus / short.opus
+                     (coefficients in, out_syn out), incl. transient frames
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+
+REF = "/root/reference"
+
+
+def synth_coef(rng, nframes, C, amp=1000.0):
+    """Random spectra shaped like real data: zero above bin 800
+    (celt_decoder_clean.c:628-636), band-decaying amplitude."""
+    k = np.arange(960)
+    env = amp / (1.0 + k / 60.0)
+    x = rng.uniform(-1, 1, (nframes, C, 960)) * env
+    x[..., 800:] = 0
+    return x.astype(np.float32)
+
+
+def main():
+    for n in (480, 60):
+        for kind in ("input", "output"):
+            shutil.copyfile(f"{REF}/test_data/ifft_{kind}_N{n}.bin", f"{HERE}/ifft_{kind}_N{n}.bin")
+
+    np.savez_compressed(f"{HERE}/ref_tables.npz", **ref.tables())
+
+    rng = np.random.default_rng(0x0B200)
+    cases = {}
+
+    def add(name, nframes, C, transient, tail):
+        coef = synth_coef(rng, nframes, C)
+        tail_in = None if not tail else rng.uniform(-500, 500, (C, 60)).astype(np.float32)
+        pcm, tail_out, _ = ref.synth_batch(coef, transient, tail_in)
+        cases[f"{name}.coef"] = coef
+        cases[f"{name}.transient"] = np.asarray(transient, np.uint8)
+        cases[f"{name}.tail_in"] = np.zeros((0,), np.float32) if tail_in is None else tail_in
+        cases[f"{name}.pcm"] = pcm
+        cases[f"{name}.tail_out"] = tail_out
+
+    add("stereo_long", 6, 2, [0] * 6, False)
+    add("stereo_short", 5, 2, [1] * 5, False)
+    add("stereo_mixed_tail", 9, 2, [0, 1, 0, 0, 1, 1, 0, 1, 0], True)
+    add("mono_mixed_tail", 7, 1, [0, 1, 1, 0, 0, 1, 0], True)
+    add("three_ch_mixed", 5, 3, [1, 0, 0, 1, 0], True)
+    add("eight_ch_mixed", 4, 8, [0, 1, 0, 1], True)
+    add("single_frame_long", 1, 2, [0], True)
+    add("single_frame_short", 1, 2, [1], False)
+    np.savez_compressed(f"{HERE}/synth_cases.npz", **cases)
+
+    calls = {}
+    for shift in range(4):
+        N2 = 960 >> shift
+        for stride in (1, 2, 4, 8):
+            inp = rng.uniform(-2000, 2000, N2 * stride).astype(np.float32)
+            out = rng.uniform(-3000, 3000, N2 + 60).astype(np.float32)
+            calls[f"s{shift}_st{stride}.in"] = inp.copy()
+            calls[f"s{shift}_st{stride}.out_before"] = out.copy()
+            ref.clt_mdct_backward(inp, out, shift, stride)
+            calls[f"s{shift}_st{stride}.out_after"] = out
+    np.savez_compressed(f"{HERE}/mdct_calls.npz", **calls)
+
+    real = {}
+    for fname, tag in (("sb-reverie.opus", "reverie"), ("sb-reverie-60ms-frames.opus", "reverie60"),
+                       ("short.opus", "short")):
+        pcm, recs = ref.decode_file(f"{REF}/test_data/{fname}", record=True)
+        # float sum in sample order after de-interleave, as examples/src/Main.cpp:131-144
+        real[f"{tag}.n_records"] = np.int64(len(recs))
+        real[f"{tag}.pcm_len"] = np.int64(pcm.size)
+        stereo20 = [i for i, r in enumerate(recs) if r["nch"] == 2 and r["coef"].shape[1] == 960]
+        tr = np.array([recs[i]["B"] == 8 for i in stereo20])
+        real[f"{tag}.n_transient"] = np.int64(tr.sum())
+        # a run of 12 consecutive LM=3 stereo frames around the first transient
+        first = int(np.argmax(tr)) if tr.any() else 0
+        lo = max(first - 5, 1)
+        idx = stereo20[lo - 1:lo + 12]          # one extra leading frame = the halo
+        assert all(b - a == 1 for a, b in zip(idx, idx[1:])), "records not consecutive"
+        real[f"{tag}.coef"] = np.stack([recs[i]["coef"] for i in idx])          # [13][2][960]
+        real[f"{tag}.transient"] = np.array([recs[i]["B"] == 8 for i in idx], np.uint8)
+        real[f"{tag}.out"] = np.stack([recs[i]["out"] for i in idx])            # [13][2][960]
+    np.savez_compressed(f"{HERE}/real_frames.npz", **real)
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
