@@ -1,0 +1,171 @@
+/* nq_celt_synth.h -- C ABI of the B200-native CELT synthesis stage
+ * (inverse MDCT + TDAC windowed overlap-add + channel interleave).
+ *
+ * Drop-in boundary for ONE path of dafx/libnyquist's bundled Opus decoder
+ * (reference paths relative to /root/reference/):
+ *
+ *   compute_inv_mdcts         third_party/opus/celt/celt_decoder_clean.c:264-312
+ *   clt_mdct_backward         third_party/opus/celt/mdct.c:267-379, proto mdct.h:66-68
+ *   clt_mdct_backward_B1_C2   third_party/opus/celt/mdct.c:258-265 (CPU), :223-243 (USE_CUDA hook)
+ *   opus_ifft                 third_party/opus/celt/kiss_fft.c:696-747
+ *   fork's GPU seam           cuda/mdct_cuda.hpp:79-103 (processMDCTCuda, processMDCTCudaB1C2,
+ *                             cleanupCudaBuffers, printCudaVersion)
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types in any signature
+ * (streams are passed as void*, i.e. a cudaStream_t).  The library has NO CPU
+ * fallback: without a CUDA device every entry fails (NQ_INTERNAL_ERROR) or,
+ * for the void reference-shaped entries, aborts loudly.
+ *
+ * Arithmetic: IEEE float32 throughout (the reference's float build,
+ * celt/arch.h:133-138).  Results match the reference within 1e-5 of full
+ * scale (32768) -- the FFT factorisation differs from kiss_fft's, so parity is
+ * tolerance-based, not bit-exact (observed ~2e-7 of full scale).
+ */
+#ifndef NQ_CELT_SYNTH_H
+#define NQ_CELT_SYNTH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define NQ_API
+#else
+#define NQ_API __attribute__((visibility("default")))
+#endif
+
+/* Error codes mirror Opus (third_party/opus/libopus/include/opus_defines.h:46-60). */
+#define NQ_OK 0
+#define NQ_BAD_ARG (-1)
+#define NQ_INTERNAL_ERROR (-3)   /* a CUDA call failed; see nq_celt_last_error() */
+#define NQ_UNIMPLEMENTED (-5)
+#define NQ_INVALID_STATE (-6)
+#define NQ_ALLOC_FAIL (-7)
+
+#define NQ_CELT_FRAME 960      /* samples per channel per 20 ms frame (LM = 3)             */
+#define NQ_CELT_HALF_OVERLAP 60 /* raw tail carried between blocks (overlap/2, mdct.c:361) */
+
+/* Per-device context: device tables, one stream, scratch buffers for the
+ * host-pointer entries.  Not re-entrant; different contexts may be used
+ * concurrently from different threads (reference threading contract:
+ * one decoder state per stream). */
+typedef struct nq_celt_ctx nq_celt_ctx;
+
+NQ_API int nq_celt_ctx_create(int device, nq_celt_ctx **out);
+NQ_API void nq_celt_ctx_destroy(nq_celt_ctx *ctx);
+NQ_API const char *nq_celt_strerror(int code);
+NQ_API const char *nq_celt_last_error(const nq_celt_ctx *ctx);
+NQ_API int nq_celt_device_count(void);
+/* Number of kernel launches issued through this context so far. */
+NQ_API long long nq_celt_launch_count(const nq_celt_ctx *ctx);
+
+/* Pinned host memory for the host-pointer batch entry (optional but needed
+ * for full PCIe bandwidth). */
+NQ_API void *nq_celt_host_alloc(size_t bytes);
+NQ_API void nq_celt_host_free(void *p);
+
+/* ---- batched synthesis: phase 2 of the restructured decoder ---------------
+ * Replaces the per-frame call compute_inv_mdcts(mode, shortBlocks, freq,
+ * out_syn, C, LM=3) at celt_decoder_clean.c:656 together with the history
+ * shift at :622-626, for nframes consecutive 20 ms frames of one stream.
+ *
+ *   coef       [nframes][C][960]  spectral coefficients exactly as
+ *              denormalise_bands leaves them in freq[] (channel-major; a
+ *              transient frame keeps its 8 sub-blocks interleaved,
+ *              freq[c*960 + j*8 + b], celt_decoder_clean.c:296)
+ *   transient  [nframes]          non-zero => shortBlocks = 8 for that frame
+ *   tail_in    [C][60] or NULL    raw tail left by the frame before the batch
+ *              (= out_syn[c][960..1020) after that frame); NULL => zeros,
+ *              i.e. a freshly reset decoder (celt_decoder_clean.c:846-859)
+ *   halo_coef  [C][960] or NULL   alternative to tail_in for a shard that
+ *              starts mid-stream: coefficients of the frame before the
+ *              batch; that frame is re-synthesised only for its tail.
+ *              Ignored when tail_in is non-NULL.
+ *   pcm_out    [nframes*960][C]   interleaved celt_sig samples (the values of
+ *              out_syn[c][0..960) per frame, before comb_filter/deemphasis)
+ *   tail_out   [C][60] or NULL    raw tail after the last frame
+ *
+ * _device: all pointers are device pointers on ctx's device, 16-byte aligned
+ * (coef, pcm_out); the work is enqueued on `stream` (NULL => ctx's stream)
+ * and the call returns without synchronising.
+ * _host: all pointers are host pointers; chunks are pipelined H2D / kernel /
+ * D2H on internal streams and the call returns when pcm_out is complete.
+ */
+NQ_API int nq_celt_synth_batch_device(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient,
+                                      const float *tail_in, const float *halo_coef, int halo_transient,
+                                      float *pcm_out, float *tail_out, int64_t nframes, int C, void *stream);
+
+NQ_API int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient,
+                                    const float *tail_in, float *pcm_out, float *tail_out,
+                                    int64_t nframes, int C);
+
+/* Same as _host, frames sharded contiguously over `ndev` devices (devices[i]
+ * = CUDA ordinal; NULL => 0..ndev-1) with one host thread + context per
+ * device and NO device-to-device traffic: a shard that starts mid-stream
+ * uploads the previous frame's coefficients as its halo. */
+NQ_API int nq_celt_synth_batch_host_multi(const int *devices, int ndev, const float *coef,
+                                          const uint8_t *transient, const float *tail_in,
+                                          float *pcm_out, float *tail_out, int64_t nframes, int C);
+
+/* ---- single-call entries with the reference's semantics -------------------
+ * nq_clt_mdct_backward == clt_mdct_backward (mdct.c:267): HOST pointers,
+ * synchronous.  `in`: N2 = (1920 >> shift)/2 coefficients at `stride`
+ * (untouched); `out`: read [0, overlap/2), written [0, N2 + overlap/2).
+ * Only the reference's static mode is supported (mdct n = 1920, overlap = 120,
+ * shift 0..3, stride >= 1); `l` and `window` may be NULL (the library owns
+ * bit-compatible tables) and are otherwise only sanity-checked.
+ * These are `void` like the reference; on any CUDA failure they print the
+ * error and abort() -- there is no CPU fallback by design. */
+typedef struct nq_mdct_lookup {   /* layout of mdct_lookup, mdct.h:49-54 */
+    int n;
+    int maxshift;
+    const void *kfft[4];
+    const float *trig;
+} nq_mdct_lookup;
+
+NQ_API void nq_clt_mdct_backward(const nq_mdct_lookup *l, float *in, float *out, const float *window,
+                                 int overlap, int shift, int stride);
+NQ_API void nq_clt_mdct_backward_B1_C2(const nq_mdct_lookup *l, float *in[2], float *out[2],
+                                       const float *window, int overlap, int shift, int stride);
+/* Error-returning form used by the two above; ctx == NULL => process-global
+ * context on the current device. */
+NQ_API int nq_celt_mdct_backward_host(nq_celt_ctx *ctx, const float *const *in, float *const *out, int ncalls,
+                                      int shift, int stride);
+
+/* opus_ifft (kiss_fft.c:696-747) with the static state mode->mdct.kfft[shift]:
+ * `count` independent N4 = 480 >> shift point UNNORMALISED inverse DFTs on
+ * interleaved (re, im) float32 host buffers, out of place (kiss_fft.c:707).
+ * This is the entry the reference's orphan golden vectors
+ * test_data/ifft_{input,output}_N{480,60}.bin pin. */
+NQ_API int nq_opus_ifft_host(nq_celt_ctx *ctx, int shift, const float *in_ri, float *out_ri, int count);
+
+/* compute_inv_mdcts (celt_decoder_clean.c:264) on host buffers: out_mem[c]
+ * points at out_syn[c]; [0,60) holds the previous raw tail on entry and
+ * [0, N*B + 60) is written.  LM in 0..3; shortBlocks = 0 or 1 << LM. */
+NQ_API int nq_compute_inv_mdcts(nq_celt_ctx *ctx, int shortBlocks, const float *X, float *const *out_mem,
+                                int C, int LM);
+
+/* ---- the fork's existing GPU seam (cuda/mdct_cuda.hpp:79-103) -------------
+ * Same names and signatures, so the reference built with -DUSE_CUDA links
+ * against this library instead of cuda/mdct_cuda.cu + cuFFT unchanged
+ * (mdct.c:223-254 calls these).  N, sine, overlap, trig and window are
+ * accepted for signature compatibility; N must be 1920 >> shift. */
+NQ_API void processMDCTCuda(const float *input, float *output, const float *trig, int N, int shift,
+                            int stride, float sine, int overlap, const float *window);
+NQ_API void processMDCTCudaB1C2(const float *input[2], float *output[2], const float *trig, int N,
+                                int shift, int stride, float sine, int overlap, const float *window);
+NQ_API void cleanupCudaBuffers(void);
+NQ_API void printCudaVersion(void);
+
+/* ---- introspection for tests ------------------------------------------- */
+/* Copies the host-built tables: t_long [16*31*2], t_short [2*30*2],
+ * window [120], trig [481] (any pointer may be NULL). */
+NQ_API void nq_celt_debug_tables(float *t_long, float *t_short, float *window, float *trig);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NQ_CELT_SYNTH_H */

@@ -1,0 +1,660 @@
+// Host layer + C ABI (include/nq_celt_synth.h) of the CELT synthesis stage.
+//
+// Mirrors, for this one path, the reference's interfaces:
+//   compute_inv_mdcts / clt_mdct_backward(_B1_C2)   celt_decoder_clean.c:264, mdct.c:258,267
+//   the fork's GPU seam processMDCTCuda*             cuda/mdct_cuda.hpp:79-103
+// and adds the batched phase-2 entry the restructured decoder calls once per
+// batch of frames.  No CPU fallback anywhere: every entry needs a CUDA device.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/nq_celt_synth.h"
+#include "celt_synth_kernels.cuh"
+
+using namespace nq;
+
+// ------------------------------------------------------------ tables -------
+namespace {
+
+struct HostTables {
+    FastTables fast;
+    GenericTables gen;
+};
+
+// The reference's sin(x)~x shortcut: sine = 2*PI*(.125f)/N in float, PI = 3.141592653f
+// (mdct.c:292, mathops.h:83).  Each of the two rotations is multiplied by (1 + j*sine).
+double ref_sine(int N) { return (double)((float)2 * 3.141592653f * (.125f) / N); }
+
+const HostTables &host_tables()
+{
+    static HostTables *T = [] {
+        HostTables *t = new HostTables();
+        const double pi = 3.14159265358979323846264338327;
+        memset(t, 0, sizeof *t);
+        // window120: modes.c:374
+        for (int i = 0; i < kOverlap; i++) {
+            const double s = sin(.5 * pi * (i + .5) / kOverlap);
+            t->fast.window[i] = t->gen.window[i] = (float)sin(.5 * pi * s * s);
+        }
+        // mdct trig: mdct.c:99, argument evaluated in float (PI is a float macro)
+        for (int i = 0; i <= 480; i++) t->gen.trig[i] = (float)cos(2 * 3.141592653f * i / kMdctN);
+        // inter-stage twiddles with both MDCT rotations folded in
+        {
+            const double s = ref_sine(1920);
+            const double gr = 1.0 - s * s, gi = 2.0 * s;   // (1 + js)^2
+            for (int n2 = 0; n2 < 16; n2++)
+                for (int k1 = 0; k1 < 30; k1++) {
+                    const double ph = 2 * pi * ((n2 + k1) / 1920.0 + (double)(n2 * k1) / 480.0);
+                    const double cr = cos(ph), ci = sin(ph);
+                    t->fast.t_long[n2 * kXRowF2 + k1] =
+                        make_float2((float)-(gr * cr - gi * ci), (float)-(gr * ci + gi * cr));
+                }
+        }
+        {
+            const double s = ref_sine(240);
+            const double gr = 1.0 - s * s, gi = 2.0 * s;
+            for (int h = 0; h < 2; h++)
+                for (int k1 = 0; k1 < 30; k1++) {
+                    const double ph = 2 * pi * ((h + k1) / 240.0 + (double)(h * k1) / 60.0);
+                    const double cr = cos(ph), ci = sin(ph);
+                    t->fast.t_short[h * 30 + k1] =
+                        make_float2((float)-(gr * cr - gi * ci), (float)-(gr * ci + gi * cr));
+                }
+        }
+        return t;
+    }();
+    return *T;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------- context -----
+struct nq_celt_ctx {
+    int device = -1;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    static constexpr int kSlots = 3;
+    cudaStream_t slot_stream[kSlots] = {};
+    cudaEvent_t kernel_done[kSlots] = {};
+    FastTables *d_fast = nullptr;
+    GenericTables *d_gen = nullptr;
+    // scratch for the host-pointer batch entry
+    float *d_in[kSlots] = {};
+    float *d_out[kSlots] = {};
+    uint8_t *d_flags[kSlots] = {};
+    size_t slot_frames_cap = 0;
+    int slot_C_cap = 0;
+    float *d_tail[2] = {};
+    float *d_halo = nullptr;
+    int tail_C_cap = 0;
+    // scratch for the single-call entries
+    float *d_call_buf = nullptr;
+    size_t call_buf_cap = 0;
+    MdctCall *d_calls = nullptr;
+    int calls_cap = 0;
+    long long launches = 0;
+    char err[512] = {0};
+};
+
+namespace {
+
+int fail(nq_celt_ctx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define NQ_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, NQ_INTERNAL_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+// Splits nframes into runs of consecutive frames, one run per warp-item.
+// Every run after the first re-computes one extra frame (its predecessor) to
+// obtain the raw tail, so runs are kept long: >= 8 frames when the batch
+// allows, and otherwise just long enough to give every resident warp one run.
+void plan_runs(long long nframes, int npairs, int num_sms, long long *frames_per_run, long long *nruns)
+{
+    const long long total_warps = (long long)num_sms * kWarpsPerCta;
+    long long target_runs = total_warps / npairs;
+    if (target_runs < 1) target_runs = 1;
+    long long K = (nframes + target_runs - 1) / target_runs;
+    if (K < 8) K = 8;
+    if (K > nframes) K = nframes > 0 ? nframes : 1;
+    *frames_per_run = K;
+    *nruns = (nframes + K - 1) / K;
+}
+
+int enqueue_synth(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const float *tail_in,
+                  const float *halo_coef, int halo_transient, float *pcm, float *tail_out, long long nframes,
+                  int C, cudaStream_t stream)
+{
+    SynthParams p;
+    memset(&p, 0, sizeof p);
+    p.coef = coef;
+    p.transient = transient;
+    p.tail_in = tail_in;
+    p.halo_coef = tail_in ? nullptr : halo_coef;
+    p.halo_transient = halo_transient ? 1 : 0;
+    p.pcm = pcm;
+    p.tail_out = tail_out;
+    p.tables = ctx->d_fast;
+    p.nframes = nframes;
+    p.C = C;
+    p.npairs = (C + 1) / 2;
+    p.flag_stride = 1;
+    p.flag_per_pair = 0;
+    plan_runs(nframes, p.npairs, ctx->num_sms, &p.frames_per_run, &p.nruns);
+    NQ_CUDA(ctx, launch_synth(p, ctx->num_sms, stream, nullptr));
+    ctx->launches++;
+    return NQ_OK;
+}
+
+std::mutex g_mu;
+nq_celt_ctx *g_ctx = nullptr;   // process-global context of the reference-shaped void entries
+
+nq_celt_ctx *global_ctx()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        int rc = nq_celt_ctx_create(dev, &g_ctx);
+        if (rc != NQ_OK) {
+            fprintf(stderr, "libnq_celt_b200: cannot create CUDA context (%s); there is no CPU fallback\n",
+                    nq_celt_strerror(rc));
+            abort();
+        }
+    }
+    return g_ctx;
+}
+
+[[noreturn]] void die(nq_celt_ctx *ctx, const char *where, int rc)
+{
+    fprintf(stderr, "libnq_celt_b200: %s failed: %s: %s\n", where, nq_celt_strerror(rc), ctx ? ctx->err : "");
+    abort();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nq_celt_strerror(int code)
+{
+    switch (code) {
+    case NQ_OK: return "success";
+    case NQ_BAD_ARG: return "invalid argument";
+    case NQ_INTERNAL_ERROR: return "CUDA error";
+    case NQ_UNIMPLEMENTED: return "unimplemented";
+    case NQ_INVALID_STATE: return "invalid state";
+    case NQ_ALLOC_FAIL: return "allocation failed";
+    default: return "unknown error";
+    }
+}
+
+const char *nq_celt_last_error(const nq_celt_ctx *ctx) { return ctx ? ctx->err : ""; }
+
+long long nq_celt_launch_count(const nq_celt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int nq_celt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void *nq_celt_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void nq_celt_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void nq_celt_debug_tables(float *t_long, float *t_short, float *window, float *trig)
+{
+    const HostTables &t = host_tables();
+    if (t_long) memcpy(t_long, t.fast.t_long, sizeof t.fast.t_long);
+    if (t_short) memcpy(t_short, t.fast.t_short, sizeof t.fast.t_short);
+    if (window) memcpy(window, t.fast.window, sizeof t.fast.window);
+    if (trig) memcpy(trig, t.gen.trig, sizeof t.gen.trig);
+}
+
+int nq_celt_ctx_create(int device, nq_celt_ctx **out)
+{
+    if (!out) return NQ_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return NQ_INTERNAL_ERROR;
+    if (device < 0 || device >= ndev) return NQ_BAD_ARG;
+    nq_celt_ctx *ctx = new (std::nothrow) nq_celt_ctx();
+    if (!ctx) return NQ_ALLOC_FAIL;
+    ctx->device = device;
+    auto bail = [&](int rc) {
+        nq_celt_ctx_destroy(ctx);
+        return rc;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    if (prop.major != 10) {
+        fprintf(stderr, "libnq_celt_b200: device %d is sm_%d%d; this library ships sm_100a code only\n", device,
+                prop.major, prop.minor);
+        return bail(NQ_INTERNAL_ERROR);
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (prepare_kernels() != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    for (int s = 0; s < nq_celt_ctx::kSlots; s++) {
+        if (cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+        if (cudaEventCreateWithFlags(&ctx->kernel_done[s], cudaEventDisableTiming) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    }
+    const HostTables &t = host_tables();
+    if (cudaMalloc(&ctx->d_fast, sizeof(FastTables)) != cudaSuccess) return bail(NQ_ALLOC_FAIL);
+    if (cudaMalloc(&ctx->d_gen, sizeof(GenericTables)) != cudaSuccess) return bail(NQ_ALLOC_FAIL);
+    if (cudaMemcpy(ctx->d_fast, &t.fast, sizeof(FastTables), cudaMemcpyHostToDevice) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    if (cudaMemcpy(ctx->d_gen, &t.gen, sizeof(GenericTables), cudaMemcpyHostToDevice) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    *out = ctx;
+    return NQ_OK;
+}
+
+void nq_celt_ctx_destroy(nq_celt_ctx *ctx)
+{
+    if (!ctx) return;
+    if (ctx->device >= 0) cudaSetDevice(ctx->device);
+    for (int s = 0; s < nq_celt_ctx::kSlots; s++) {
+        if (ctx->slot_stream[s]) { cudaStreamSynchronize(ctx->slot_stream[s]); cudaStreamDestroy(ctx->slot_stream[s]); }
+        if (ctx->kernel_done[s]) cudaEventDestroy(ctx->kernel_done[s]);
+        cudaFree(ctx->d_in[s]);
+        cudaFree(ctx->d_out[s]);
+        cudaFree(ctx->d_flags[s]);
+    }
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    cudaFree(ctx->d_tail[0]);
+    cudaFree(ctx->d_tail[1]);
+    cudaFree(ctx->d_halo);
+    cudaFree(ctx->d_call_buf);
+    cudaFree(ctx->d_calls);
+    cudaFree(ctx->d_fast);
+    cudaFree(ctx->d_gen);
+    delete ctx;
+}
+
+int nq_celt_synth_batch_device(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const float *tail_in,
+                               const float *halo_coef, int halo_transient, float *pcm_out, float *tail_out,
+                               int64_t nframes, int C, void *stream)
+{
+    if (!ctx) return NQ_BAD_ARG;
+    if (nframes < 0 || C < 1 || C > 255) return fail(ctx, NQ_BAD_ARG, "nframes=%lld C=%d out of range", (long long)nframes, C);
+    if (nframes == 0) {
+        // nothing to synthesise: the tail passes through unchanged
+        if (tail_out) {
+            NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+            cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+            if (tail_in) NQ_CUDA(ctx, cudaMemcpyAsync(tail_out, tail_in, sizeof(float) * C * kHalfOvl, cudaMemcpyDeviceToDevice, st));
+            else NQ_CUDA(ctx, cudaMemsetAsync(tail_out, 0, sizeof(float) * C * kHalfOvl, st));
+        }
+        return NQ_OK;
+    }
+    if (!coef || !transient || !pcm_out) return fail(ctx, NQ_BAD_ARG, "null coef/transient/pcm_out");
+    if ((reinterpret_cast<uintptr_t>(coef) & 15) || (reinterpret_cast<uintptr_t>(pcm_out) & 15) ||
+        (halo_coef && (reinterpret_cast<uintptr_t>(halo_coef) & 15)))
+        return fail(ctx, NQ_BAD_ARG, "coef, halo_coef and pcm_out must be 16-byte aligned device pointers");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    return enqueue_synth(ctx, coef, transient, tail_in, halo_coef, halo_transient, pcm_out, tail_out, nframes, C,
+                         stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+}  // extern "C"
+
+namespace {
+
+// Host-pointer batch over [0, nframes) with an optional host halo frame.
+int synth_host_range(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const float *tail_in,
+                     const float *halo_coef, int halo_transient, float *pcm_out, float *tail_out,
+                     long long nframes, int C)
+{
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    constexpr int S = nq_celt_ctx::kSlots;
+    const size_t row = (size_t)C * kFrame;
+    // chunk size: ~64 MB of coefficients per slot, enough frames to fill the GPU
+    long long chunk = (long long)((64u << 20) / (row * sizeof(float)));
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > nframes) chunk = nframes;
+    if ((size_t)chunk > ctx->slot_frames_cap || C > ctx->slot_C_cap) {
+        for (int s = 0; s < S; s++) {
+            NQ_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+            cudaFree(ctx->d_in[s]); cudaFree(ctx->d_out[s]); cudaFree(ctx->d_flags[s]);
+            ctx->d_in[s] = ctx->d_out[s] = nullptr; ctx->d_flags[s] = nullptr;
+        }
+        ctx->slot_frames_cap = 0;
+        for (int s = 0; s < S; s++) {
+            if (cudaMalloc(&ctx->d_in[s], chunk * row * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&ctx->d_out[s], chunk * row * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&ctx->d_flags[s], chunk) != cudaSuccess)
+                return fail(ctx, NQ_ALLOC_FAIL, "device scratch for %lld frames x %d channels", chunk, C);
+        }
+        ctx->slot_frames_cap = (size_t)chunk;
+        ctx->slot_C_cap = C;
+    }
+    if (C > ctx->tail_C_cap) {
+        cudaFree(ctx->d_tail[0]); cudaFree(ctx->d_tail[1]); cudaFree(ctx->d_halo);
+        ctx->d_tail[0] = ctx->d_tail[1] = ctx->d_halo = nullptr;
+        ctx->tail_C_cap = 0;
+        if (cudaMalloc(&ctx->d_tail[0], sizeof(float) * C * kHalfOvl) != cudaSuccess ||
+            cudaMalloc(&ctx->d_tail[1], sizeof(float) * C * kHalfOvl) != cudaSuccess ||
+            cudaMalloc(&ctx->d_halo, sizeof(float) * row) != cudaSuccess)
+            return fail(ctx, NQ_ALLOC_FAIL, "device tail buffers");
+        ctx->tail_C_cap = C;
+    }
+    const size_t tail_bytes = sizeof(float) * C * kHalfOvl;
+    // chunk i reads its initial tail from d_tail[(i+1)&1] and leaves its final tail in d_tail[i&1]
+    const bool use_halo = !tail_in && halo_coef;
+    if (tail_in) NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_tail[1], tail_in, tail_bytes, cudaMemcpyHostToDevice, ctx->slot_stream[0]));
+    else NQ_CUDA(ctx, cudaMemsetAsync(ctx->d_tail[1], 0, tail_bytes, ctx->slot_stream[0]));
+    if (use_halo) NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_halo, halo_coef, row * sizeof(float), cudaMemcpyHostToDevice, ctx->slot_stream[0]));
+
+    long long nchunks = (nframes + chunk - 1) / chunk;
+    for (long long i = 0; i < nchunks; i++) {
+        const int s = (int)(i % S);
+        cudaStream_t st = ctx->slot_stream[s];
+        const long long f0 = i * chunk, n = (f0 + chunk <= nframes) ? chunk : nframes - f0;
+        NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_in[s], coef + f0 * row, n * row * sizeof(float), cudaMemcpyHostToDevice, st));
+        NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags[s], transient + f0, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (i > 0) NQ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->kernel_done[(i - 1) % S], 0));
+        const bool first_with_halo = (i == 0 && use_halo);
+        int rc = enqueue_synth(ctx, ctx->d_in[s], ctx->d_flags[s], first_with_halo ? nullptr : ctx->d_tail[(i + 1) & 1],
+                               first_with_halo ? ctx->d_halo : nullptr, halo_transient, ctx->d_out[s],
+                               ctx->d_tail[i & 1], n, C, st);
+        if (rc != NQ_OK) return rc;
+        NQ_CUDA(ctx, cudaEventRecord(ctx->kernel_done[s], st));
+        NQ_CUDA(ctx, cudaMemcpyAsync(pcm_out + f0 * row, ctx->d_out[s], n * row * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (i == nchunks - 1 && tail_out)
+            NQ_CUDA(ctx, cudaMemcpyAsync(tail_out, ctx->d_tail[i & 1], tail_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < S; s++) NQ_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+    return NQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const float *tail_in,
+                             float *pcm_out, float *tail_out, int64_t nframes, int C)
+{
+    if (!ctx) return NQ_BAD_ARG;
+    if (nframes < 0 || C < 1 || C > 255) return fail(ctx, NQ_BAD_ARG, "nframes=%lld C=%d out of range", (long long)nframes, C);
+    if (nframes == 0) {
+        if (tail_out) {
+            if (tail_in) memcpy(tail_out, tail_in, sizeof(float) * C * kHalfOvl);
+            else memset(tail_out, 0, sizeof(float) * C * kHalfOvl);
+        }
+        return NQ_OK;
+    }
+    if (!coef || !transient || !pcm_out) return fail(ctx, NQ_BAD_ARG, "null coef/transient/pcm_out");
+    return synth_host_range(ctx, coef, transient, tail_in, nullptr, 0, pcm_out, tail_out, nframes, C);
+}
+
+int nq_celt_synth_batch_host_multi(const int *devices, int ndev, const float *coef, const uint8_t *transient,
+                                   const float *tail_in, float *pcm_out, float *tail_out, int64_t nframes, int C)
+{
+    if (ndev < 1 || nframes < 0 || C < 1 || C > 255) return NQ_BAD_ARG;
+    if (nframes == 0) {
+        if (tail_out) {
+            if (tail_in) memcpy(tail_out, tail_in, sizeof(float) * C * kHalfOvl);
+            else memset(tail_out, 0, sizeof(float) * C * kHalfOvl);
+        }
+        return NQ_OK;
+    }
+    if (!coef || !transient || !pcm_out) return NQ_BAD_ARG;
+    if (ndev > nframes) ndev = (int)nframes;
+    std::vector<int> rcs(ndev, NQ_OK);
+    std::vector<std::thread> th;
+    const size_t row = (size_t)C * kFrame;
+    for (int d = 0; d < ndev; d++) {
+        th.emplace_back([&, d] {
+            nq_celt_ctx *ctx = nullptr;
+            int rc = nq_celt_ctx_create(devices ? devices[d] : d, &ctx);
+            if (rc == NQ_OK) {
+                // contiguous, disjoint frame ranges; no collective, no peer traffic
+                const long long f0 = nframes * d / ndev, f1 = nframes * (d + 1) / ndev;
+                rc = synth_host_range(ctx, coef + f0 * row, transient + f0, f0 == 0 ? tail_in : nullptr,
+                                      f0 > 0 ? coef + (f0 - 1) * row : nullptr, f0 > 0 ? transient[f0 - 1] : 0,
+                                      pcm_out + f0 * row, d == ndev - 1 ? tail_out : nullptr, f1 - f0, C);
+                if (rc != NQ_OK) fprintf(stderr, "libnq_celt_b200: device %d: %s\n", d, ctx->err);
+            }
+            nq_celt_ctx_destroy(ctx);
+            rcs[d] = rc;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int rc : rcs)
+        if (rc != NQ_OK) return rc;
+    return NQ_OK;
+}
+
+// ------------------------------------------------- single-call entries -----
+int nq_celt_mdct_backward_host(nq_celt_ctx *ctx, const float *const *in, float *const *out, int ncalls, int shift,
+                               int stride)
+{
+    if (!ctx) ctx = global_ctx();
+    if (ncalls < 1 || shift < 0 || shift > 3 || stride < 1 || !in || !out)
+        return fail(ctx, NQ_BAD_ARG, "ncalls=%d shift=%d stride=%d", ncalls, shift, stride);
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int N2 = (kMdctN >> shift) >> 1;
+    const size_t in_span = (size_t)(N2 - 1) * stride + 1;
+    const size_t in_pad = (in_span + 3) & ~(size_t)3, out_len = (size_t)N2 + kHalfOvl;
+    const size_t per_call = in_pad + out_len;
+    if (per_call * ncalls > ctx->call_buf_cap) {
+        cudaFree(ctx->d_call_buf);
+        ctx->d_call_buf = nullptr;
+        ctx->call_buf_cap = 0;
+        if (cudaMalloc(&ctx->d_call_buf, per_call * ncalls * sizeof(float)) != cudaSuccess)
+            return fail(ctx, NQ_ALLOC_FAIL, "call scratch");
+        ctx->call_buf_cap = per_call * ncalls;
+    }
+    if (ncalls > ctx->calls_cap) {
+        cudaFree(ctx->d_calls);
+        ctx->d_calls = nullptr;
+        ctx->calls_cap = 0;
+        if (cudaMalloc(&ctx->d_calls, sizeof(MdctCall) * ncalls) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "call table");
+        ctx->calls_cap = ncalls;
+    }
+    std::vector<MdctCall> calls(ncalls);
+    cudaStream_t st = ctx->stream;
+    for (int i = 0; i < ncalls; i++) {
+        float *d_in = ctx->d_call_buf + per_call * i, *d_out = d_in + in_pad;
+        calls[i] = MdctCall{d_in, d_out, shift, stride, 0};
+        NQ_CUDA(ctx, cudaMemcpyAsync(d_in, in[i], in_span * sizeof(float), cudaMemcpyHostToDevice, st));
+        NQ_CUDA(ctx, cudaMemcpyAsync(d_out, out[i], kHalfOvl * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_calls, calls.data(), sizeof(MdctCall) * ncalls, cudaMemcpyHostToDevice, st));
+    NQ_CUDA(ctx, launch_mdct_generic(ctx->d_calls, ncalls, ctx->d_gen, st));
+    ctx->launches++;
+    for (int i = 0; i < ncalls; i++)
+        NQ_CUDA(ctx, cudaMemcpyAsync(out[i], calls[i].out, out_len * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NQ_CUDA(ctx, cudaStreamSynchronize(st));
+    return NQ_OK;
+}
+
+// opus_ifft (kiss_fft.c:696) with the static state kfft[shift]: `count` independent
+// N4 = 480 >> shift point unnormalised inverse DFTs, interleaved re/im, host pointers.
+int nq_opus_ifft_host(nq_celt_ctx *ctx, int shift, const float *in_ri, float *out_ri, int count)
+{
+    if (!ctx) ctx = global_ctx();
+    if (shift < 0 || shift > 3 || count < 1 || !in_ri || !out_ri || in_ri == out_ri)
+        return fail(ctx, NQ_BAD_ARG, "shift=%d count=%d (in-place not supported, kiss_fft.c:707)", shift, count);
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)2 * (480 >> shift);
+    if (2 * n * count > ctx->call_buf_cap) {
+        cudaFree(ctx->d_call_buf);
+        ctx->d_call_buf = nullptr;
+        ctx->call_buf_cap = 0;
+        if (cudaMalloc(&ctx->d_call_buf, 2 * n * count * sizeof(float)) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "call scratch");
+        ctx->call_buf_cap = 2 * n * count;
+    }
+    if (count > ctx->calls_cap) {
+        cudaFree(ctx->d_calls);
+        ctx->d_calls = nullptr;
+        ctx->calls_cap = 0;
+        if (cudaMalloc(&ctx->d_calls, sizeof(MdctCall) * count) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "call table");
+        ctx->calls_cap = count;
+    }
+    cudaStream_t st = ctx->stream;
+    float *d_in = ctx->d_call_buf, *d_out = ctx->d_call_buf + n * count;
+    std::vector<MdctCall> calls(count);
+    for (int i = 0; i < count; i++) calls[i] = MdctCall{d_in + n * i, d_out + n * i, shift, 1, 1};
+    NQ_CUDA(ctx, cudaMemcpyAsync(d_in, in_ri, n * count * sizeof(float), cudaMemcpyHostToDevice, st));
+    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_calls, calls.data(), sizeof(MdctCall) * count, cudaMemcpyHostToDevice, st));
+    NQ_CUDA(ctx, launch_mdct_generic(ctx->d_calls, count, ctx->d_gen, st));
+    ctx->launches++;
+    NQ_CUDA(ctx, cudaMemcpyAsync(out_ri, d_out, n * count * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NQ_CUDA(ctx, cudaStreamSynchronize(st));
+    return NQ_OK;
+}
+
+static void check_static_mode(const nq_mdct_lookup *l, int overlap, int shift)
+{
+    if ((l && l->n != kMdctN) || overlap != kOverlap || shift < 0 || shift > 3) {
+        fprintf(stderr, "libnq_celt_b200: only the static 48 kHz mode is supported (mdct n=1920, overlap=120, shift 0..3); "
+                        "got n=%d overlap=%d shift=%d\n", l ? l->n : kMdctN, overlap, shift);
+        abort();
+    }
+}
+
+void nq_clt_mdct_backward(const nq_mdct_lookup *l, float *in, float *out, const float *window, int overlap, int shift,
+                          int stride)
+{
+    (void)window;
+    check_static_mode(l, overlap, shift);
+    nq_celt_ctx *ctx = global_ctx();
+    const float *ins[1] = {in};
+    float *outs[1] = {out};
+    int rc = nq_celt_mdct_backward_host(ctx, ins, outs, 1, shift, stride);
+    if (rc != NQ_OK) die(ctx, "clt_mdct_backward", rc);
+}
+
+void nq_clt_mdct_backward_B1_C2(const nq_mdct_lookup *l, float *in[2], float *out[2], const float *window, int overlap,
+                                int shift, int stride)
+{
+    (void)window;
+    check_static_mode(l, overlap, shift);
+    nq_celt_ctx *ctx = global_ctx();
+    int rc = nq_celt_mdct_backward_host(ctx, in, out, 2, shift, stride);
+    if (rc != NQ_OK) die(ctx, "clt_mdct_backward_B1_C2", rc);
+}
+
+int nq_compute_inv_mdcts(nq_celt_ctx *ctx, int shortBlocks, const float *X, float *const *out_mem, int C, int LM)
+{
+    if (!ctx) ctx = global_ctx();
+    if (!X || !out_mem || C < 1 || C > 255 || LM < 0 || LM > 3 || (shortBlocks != 0 && shortBlocks != (1 << LM)))
+        return fail(ctx, NQ_BAD_ARG, "shortBlocks=%d C=%d LM=%d", shortBlocks, C, LM);
+    // celt_decoder_clean.c:273-284
+    int B, N, shift;
+    if (shortBlocks) { B = shortBlocks; N = 120; shift = 3; }
+    else { B = 1; N = 120 << LM; shift = 3 - LM; }
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t xlen = (size_t)N * B, olen = xlen + kHalfOvl;
+    const size_t xpad = (xlen + 3) & ~(size_t)3, opad = (olen + 3) & ~(size_t)3;
+    const size_t need = (xpad + opad) * C;
+    if (need > ctx->call_buf_cap) {
+        cudaFree(ctx->d_call_buf);
+        ctx->d_call_buf = nullptr;
+        ctx->call_buf_cap = 0;
+        if (cudaMalloc(&ctx->d_call_buf, need * sizeof(float)) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "call scratch");
+        ctx->call_buf_cap = need;
+    }
+    if (C * B > ctx->calls_cap) {
+        cudaFree(ctx->d_calls);
+        ctx->d_calls = nullptr;
+        ctx->calls_cap = 0;
+        if (cudaMalloc(&ctx->d_calls, sizeof(MdctCall) * C * B) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "call table");
+        ctx->calls_cap = C * B;
+    }
+    cudaStream_t st = ctx->stream;
+    float *d_x = ctx->d_call_buf, *d_o = ctx->d_call_buf + xpad * C;
+    NQ_CUDA(ctx, cudaMemcpyAsync(d_x, X, xlen * C * sizeof(float), cudaMemcpyHostToDevice, st));   // X is [C][N*B] contiguous
+    std::vector<MdctCall> calls((size_t)C * B);
+    for (int c = 0; c < C; c++) {
+        NQ_CUDA(ctx, cudaMemcpyAsync(d_o + opad * c, out_mem[c], kHalfOvl * sizeof(float), cudaMemcpyHostToDevice, st));
+        for (int b = 0; b < B; b++)   // celt_decoder_clean.c:296-298,309: in = X + b + c*N*B, out = out_mem[c] + N*b, stride B
+            calls[(size_t)b * C + c] = MdctCall{d_x + xlen * c + b, d_o + opad * c + (size_t)N * b, shift, B, 0};
+    }
+    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_calls, calls.data(), sizeof(MdctCall) * calls.size(), cudaMemcpyHostToDevice, st));
+    // sub-block b+1 consumes the raw tail sub-block b leaves behind: B launches in stream order, C calls each
+    for (int b = 0; b < B; b++) {
+        NQ_CUDA(ctx, launch_mdct_generic(ctx->d_calls + (size_t)b * C, C, ctx->d_gen, st));
+        ctx->launches++;
+    }
+    for (int c = 0; c < C; c++)
+        NQ_CUDA(ctx, cudaMemcpyAsync(out_mem[c], d_o + opad * c, olen * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NQ_CUDA(ctx, cudaStreamSynchronize(st));
+    return NQ_OK;
+}
+
+// ------------------------------------------ fork seam, cuda/mdct_cuda.hpp --
+void processMDCTCuda(const float *input, float *output, const float *trig, int N, int shift, int stride, float sine,
+                     int overlap, const float *window)
+{
+    (void)trig; (void)sine; (void)window;
+    if (N != (kMdctN >> shift)) {
+        fprintf(stderr, "libnq_celt_b200: processMDCTCuda: N=%d does not match 1920 >> shift (%d)\n", N, shift);
+        abort();
+    }
+    check_static_mode(nullptr, overlap, shift);
+    nq_celt_ctx *ctx = global_ctx();
+    const float *ins[1] = {input};
+    float *outs[1] = {output};
+    int rc = nq_celt_mdct_backward_host(ctx, ins, outs, 1, shift, stride);
+    if (rc != NQ_OK) die(ctx, "processMDCTCuda", rc);
+}
+
+void processMDCTCudaB1C2(const float *input[2], float *output[2], const float *trig, int N, int shift, int stride,
+                         float sine, int overlap, const float *window)
+{
+    (void)trig; (void)sine; (void)window;
+    if (N != (kMdctN >> shift)) {
+        fprintf(stderr, "libnq_celt_b200: processMDCTCudaB1C2: N=%d does not match 1920 >> shift (%d)\n", N, shift);
+        abort();
+    }
+    check_static_mode(nullptr, overlap, shift);
+    nq_celt_ctx *ctx = global_ctx();
+    int rc = nq_celt_mdct_backward_host(ctx, input, output, 2, shift, stride);
+    if (rc != NQ_OK) die(ctx, "processMDCTCudaB1C2", rc);
+}
+
+void cleanupCudaBuffers(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    nq_celt_ctx_destroy(g_ctx);
+    g_ctx = nullptr;
+}
+
+void printCudaVersion(void)
+{
+    int rt = 0, drv = 0;
+    cudaRuntimeGetVersion(&rt);
+    cudaDriverGetVersion(&drv);
+    printf("libnq_celt_b200 (sm_100a): CUDA runtime %d, driver %d\n", rt, drv);
+}
+
+}  // extern "C"

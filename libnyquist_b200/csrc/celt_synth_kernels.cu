@@ -1,0 +1,497 @@
+// CELT synthesis (inverse MDCT + TDAC windowed overlap-add) for sm_100a.
+//
+// What the reference does per frame (third_party/opus/celt/):
+//   compute_inv_mdcts     celt_decoder_clean.c:264-312  long: 1 x N2=960, transient: 8 x N2=120 at stride 8
+//   clt_mdct_backward     mdct.c:267-379   pre-rotate :295-313, opus_ifft :316, post-rotate :320-359, mirror :361-377
+//   opus_ifft             kiss_fft.c:696-747
+//   tail hand-over        celt_decoder_clean.c:622-626 (the 60-sample raw tail lives in decode_mem)
+//
+// B200 design: the path is HBM-bound (15 360 B per stereo
+// frame, ~4 flop/B), so the kernel is organised around moving every sample
+// across HBM exactly once:
+//   * one WARP owns a run of consecutive frames of one channel pair and keeps
+//     the 60-sample raw tail on chip between frames (a run that does not
+//     start the batch re-computes the frame before it instead of reading a
+//     tail from memory);
+//   * the frame's two 3840-byte coefficient rows arrive by TMA bulk copy
+//     (cp.async.bulk + mbarrier) into a warp-private shared-memory buffer,
+//     prefetched one frame ahead while the current frame is being computed;
+//   * the 480-point inverse FFT is 30 x 16: stage 1 = 32 lanes x (30-point
+//     prime-factor DFT in registers), one padded, conflict-free shared-memory
+//     transpose, stage 2 = 30 lanes x 2 channels x (16-point DFT in
+//     registers).  The MDCT pre-/post-rotations (incl. the reference's
+//     sin(x)~x factor (1+js)^2) are folded into the single inter-stage
+//     twiddle table plus literal per-slot rotations, so there is one table
+//     load per complex point;
+//   * front/back input pairing and even/odd output pairing are done with one
+//     warp shuffle per point (bins i and N4-1-i live in mirrored lanes);
+//   * window, overlap-add and the stereo channel interleave are fused into
+//     the epilogue: each lane stores float4 = {L[n], R[n], L[n+1], R[n+1]},
+//     30 lanes writing 480 contiguous bytes per instruction.
+//   * transient frames (8 short blocks): lanes = (channel, sub-block, half),
+//     60 = 30 x 2, the radix-2 step and the sub-block to sub-block tail are
+//     warp shuffles; output is staged through the transpose buffer so global
+//     stores stay 128-bit and coalesced.
+// No tensor cores: this is an FFT, not a dense contraction.
+#include "celt_synth_kernels.cuh"
+#include "celt_fft_codelets.cuh"
+
+namespace nq {
+
+// ------------------------------------------------------------------ PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
+__device__ __forceinline__ void tma_load_row(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct __align__(16) WarpSmem {
+    float in[2 * kInRowFloats];       // two coefficient rows (TMA destination)
+    float2 x[2 * kXChanF2];           // inter-stage transpose buffer / short-frame output staging
+    float tail[2 * kHalfOvl];         // raw tail y[N2-60..N2) of the previous (sub-)block, per channel
+    unsigned long long bar;           // mbarrier for the TMA prefetch
+    unsigned long long pad_;
+};
+static_assert(sizeof(WarpSmem) % 16 == 0, "warp smem slice must keep 16-byte alignment");
+static_assert((kInRowFloats * 4) % 16 == 0, "TMA destination rows must be 16-byte aligned");
+
+size_t fast_kernel_smem_bytes() { return sizeof(FastTables) + kWarpsPerCta * sizeof(WarpSmem); }
+
+// ------------------------------------------------------------ long frame ---
+// One stereo (or mono: nch == 1) long block per call.  See file header.
+template <bool kStereo>
+__device__ __forceinline__ void long_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long f,
+                                           int cb, int nch, bool store, bool more, long long fnext,
+                                           const float (&w4)[4])
+{
+    constexpr float pre_re[30] = {NQ_PRE30_RE};
+    constexpr float pre_im[30] = {NQ_PRE30_IM};
+    constexpr float post_re[16] = {NQ_POST16_RE};
+    constexpr float post_im[16] = {NQ_POST16_IM};
+
+    // ---- stage 1: lane = (channel c1, residue n2); bins i = 16*n1 + n2 ----
+    const int c1 = lane >> 4, n2 = lane & 15;
+    float2 g[30];
+    {
+        const float2 *row = reinterpret_cast<const float2 *>(ws.in + c1 * kInRowFloats) + n2;
+        float2 v[30];
+#pragma unroll
+        for (int n1 = 0; n1 < 30; n1++) v[n1] = row[16 * n1];   // (X[2i], X[2i+1])
+        // X[N2-1-2i] is the odd element of bin 479-i = 16*(29-n1) + (15-n2): mirrored lane, mirrored slot
+#pragma unroll
+        for (int n1 = 0; n1 < 30; n1++) {
+            const float xb = __shfl_xor_sync(kFull, v[29 - n1].y, 15);
+            const float xa = v[n1].x;
+            // (xb + j xa) * exp(j 2pi n1 / 120)   [mdct.c:303-312 without the lane-constant part]
+            g[n1] = make_float2(fmaf(xb, pre_re[n1], -(xa * pre_im[n1])), fmaf(xb, pre_im[n1], xa * pre_re[n1]));
+        }
+    }
+    idft30(g);
+    {
+        const float2 *tw = tb.t_long + n2 * kXRowF2;
+        float2 *dst = ws.x + c1 * kXChanF2 + n2 * kXRowF2;
+#pragma unroll
+        for (int k1 = 0; k1 < 30; k1++) dst[k1] = cmul(g[k1], tw[k1]);
+    }
+    __syncwarp();
+    // every lane has consumed its part of ws.in: prefetch the next frame
+    if (more && lane == 0) {
+        mbar_expect_tx(&ws.bar, nch * kFrame * 4);
+        for (int ch = 0; ch < nch; ch++) {
+            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.C * kFrame) + (cb + ch) * kFrame;
+            tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
+        }
+    }
+
+    // ---- stage 2: lane = k1 (30 active); bins k = k1 + 30*k2, both channels ----
+    const bool active = lane < 30;
+    const int k1 = active ? lane : 29;
+    float E[2][16], O[2][16], H0[2], H1[2];
+    float2 told[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+        if (ch < nch) {
+            told[ch] = *reinterpret_cast<const float2 *>(ws.tail + ch * kHalfOvl + 58 - 2 * k1);
+            float2 z[16];
+            const float2 *src = ws.x + ch * kXChanF2 + k1;
+#pragma unroll
+            for (int q = 0; q < 16; q++) z[q] = src[q * kXRowF2];
+            idft16(z);
+            float im[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                // Y = Z * exp(j 2pi k2/64); y[2k] = -Re Y, y[959-2k] = Im Y   [mdct.c:330-358]
+                const float2 zz = z[slot16(k2)];
+                E[ch][k2] = fmaf(zz.y, post_im[k2], -(zz.x * post_re[k2]));
+                im[k2] = fmaf(zz.x, post_im[k2], zz.y * post_re[k2]);
+            }
+            // y[2k+1] = y[959-2k'] with k' = 479-k = (29-k1) + 30*(15-k2)
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) O[ch][k2] = __shfl_sync(kFull, im[15 - k2], (29 - lane) & 31);
+        }
+    }
+    __syncwarp();   // all lanes are done with ws.x and with the old tail
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+        if (ch < nch) {
+            if (active)   // raw tail for the next frame: y[900+2k1], y[901+2k1]
+                *reinterpret_cast<float2 *>(ws.tail + ch * kHalfOvl + 2 * k1) = make_float2(E[ch][15], O[ch][15]);
+            // TDAC mirror with the previous raw tail [mdct.c:361-377]; m = 2k1 and 2k1+1
+            const float t0 = told[ch].y, t1 = told[ch].x;   // tail[59-2k1], tail[58-2k1]
+            const float y0 = E[ch][0], y1 = O[ch][0];
+            E[ch][0] = fmaf(w4[0], t0, w4[1] * y0);      // out[60+2k1] = w[59-2k1] t0 + w[60+2k1] y0
+            O[ch][0] = fmaf(w4[2], t1, w4[3] * y1);      // out[61+2k1] = w[58-2k1] t1 + w[61+2k1] y1
+            H0[ch] = fmaf(w4[3], t1, -(w4[2] * y1));     // out[58-2k1] = w[61+2k1] t1 - w[58-2k1] y1
+            H1[ch] = fmaf(w4[1], t0, -(w4[0] * y0));     // out[59-2k1] = w[60+2k1] t0 - w[59-2k1] y0
+        }
+    }
+    if (store && active) {
+        if (kStereo) {
+            float4 *dst = reinterpret_cast<float4 *>(p.pcm + f * (kFrame * 2));
+            __stcs(dst + 29 - k1, make_float4(H0[0], H0[1], H1[0], H1[1]));
+#pragma unroll
+            for (int k2 = 0; k2 < 15; k2++)
+                __stcs(dst + 30 + k1 + 30 * k2, make_float4(E[0][k2], E[1][k2], O[0][k2], O[1][k2]));
+        } else {
+            float *dst = p.pcm + f * kFrame * p.C + cb;
+            const int C = p.C;
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch < nch) {
+                    dst[(58 - 2 * k1) * C + ch] = H0[ch];
+                    dst[(59 - 2 * k1) * C + ch] = H1[ch];
+#pragma unroll
+                    for (int k2 = 0; k2 < 15; k2++) {
+                        const int n = 60 + 2 * (k1 + 30 * k2);
+                        dst[n * C + ch] = E[ch][k2];
+                        dst[(n + 1) * C + ch] = O[ch][k2];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------ transient frame ----
+// 8 short blocks per channel (N = 240, N2 = 120, N4 = 60), sub-block b uses
+// coefficients X[b + 8j] (celt_decoder_clean.c:292-300).
+template <bool kStereo>
+__device__ __forceinline__ void short_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long f,
+                                            int cb, int nch, bool store, bool more, long long fnext)
+{
+    constexpr float pre_re[30] = {NQ_PRE30_RE};
+    constexpr float pre_im[30] = {NQ_PRE30_IM};
+
+    // lane = (channel c, sub-block b, half h); bins i = 2*n1 + h
+    const int c = lane >> 4, b = (lane >> 1) & 7, h = lane & 1;
+    float2 g[30];
+    {
+        const float *row = ws.in + c * kInRowFloats + b;
+#pragma unroll
+        for (int n1 = 0; n1 < 30; n1++) {
+            const float xa = row[32 * n1 + 16 * h];              // x[2i]     = X[b + 8*2i]
+            const float xb = row[952 - 32 * n1 - 16 * h];        // x[119-2i] = X[b + 8*(119-2i)]
+            g[n1] = make_float2(fmaf(xb, pre_re[n1], -(xa * pre_im[n1])), fmaf(xb, pre_im[n1], xa * pre_re[n1]));
+        }
+    }
+    idft30(g);
+    // radix-2 step across the lane pair (h = 0, 1); bins k = k1 + 30*h
+    // Y = Z * exp(j 2pi 30 h / 240); y[2k] = -Re Y, y[119-2k] = Im Y
+    // h = 0: head[k1] = y[2k1],      tl[k1] = y[119-2k1]
+    // h = 1: head[k1] = y[59-2k1],   tl[k1] = y[60+2k1]
+    float head[30], tl[30];
+    {
+        const float2 *tw = tb.t_short + h * 30;
+        const float dr = h ? NQ_SQRT1_2 : 1.0f, di = h ? NQ_SQRT1_2 : 0.0f;
+#pragma unroll
+        for (int k1 = 0; k1 < 30; k1++) {
+            const float2 a = cmul(g[k1], tw[k1]);
+            const float2 pa = make_float2(__shfl_xor_sync(kFull, a.x, 1), __shfl_xor_sync(kFull, a.y, 1));
+            const float2 z = h ? csub(pa, a) : cadd(a, pa);
+            const float yr = fmaf(z.x, dr, -(z.y * di)), yi = fmaf(z.x, di, z.y * dr);
+            head[k1] = h ? yi : -yr;
+            tl[k1] = h ? -yr : yi;
+        }
+    }
+    __syncwarp();
+    if (more && lane == 0) {
+        mbar_expect_tx(&ws.bar, nch * kFrame * 4);
+        for (int ch = 0; ch < nch; ch++) {
+            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.C * kFrame) + (cb + ch) * kFrame;
+            tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
+        }
+    }
+    // window + overlap-add against the previous sub-block's raw tail
+    float *stage = reinterpret_cast<float *>(ws.x);   // [n][2] interleaved
+#pragma unroll
+    for (int k1 = 0; k1 < 30; k1++) {
+        const int m = h ? 59 - 2 * k1 : 2 * k1;      // head[k1] = y[m]
+        float tp = __shfl_up_sync(kFull, tl[k1], 2);  // same (c, h), sub-block b-1
+        if (b == 0) tp = ws.tail[c * kHalfOvl + 59 - m];
+        const float wlo = tb.window[59 - m], whi = tb.window[60 + m];
+        const float olo = fmaf(whi, tp, -(wlo * head[k1]));   // out[59-m]
+        const float ohi = fmaf(wlo, tp, whi * head[k1]);      // out[60+m]
+        stage[(120 * b + 59 - m) * 2 + c] = olo;
+        stage[(120 * b + 60 + m) * 2 + c] = ohi;
+    }
+    __syncwarp();   // old frame tail fully consumed, staging complete
+    if (b == 7) {
+#pragma unroll
+        for (int k1 = 0; k1 < 30; k1++) {
+            const int m = h ? 59 - 2 * k1 : 2 * k1;
+            ws.tail[c * kHalfOvl + 59 - m] = tl[k1];          // y_7[60 + (59-m)]
+        }
+    }
+    if (store) {
+        if (kStereo) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+            float4 *dst = reinterpret_cast<float4 *>(p.pcm + f * (kFrame * 2));
+#pragma unroll
+            for (int j = 0; j < 15; j++) __stcs(dst + lane + 32 * j, s4[lane + 32 * j]);
+        } else {
+            float *dst = p.pcm + f * kFrame * p.C + cb;
+            for (int idx = lane; idx < 2 * kFrame; idx += 32) {
+                const int n = idx >> 1, ch = idx & 1;
+                if (ch < nch) dst[n * p.C + ch] = stage[idx];
+            }
+        }
+    }
+    __syncwarp();   // staging buffer is reused by the next frame's stage 1
+}
+
+// ----------------------------------------------------------- fast kernel ---
+template <bool kStereo>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) celt_synth_kernel(const __grid_constant__ SynthParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastTables &tb = *reinterpret_cast<FastTables *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem &ws = reinterpret_cast<WarpSmem *>(smem_raw + sizeof(FastTables))[warp];
+
+    {
+        const float *src = reinterpret_cast<const float *>(p.tables);
+        float *dst = reinterpret_cast<float *>(&tb);
+        for (int i = threadIdx.x; i < int(sizeof(FastTables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    for (int i = lane; i < 2 * kInRowFloats; i += 32) ws.in[i] = 0.f;
+    if (lane == 0) {
+        mbar_init(&ws.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    // lane-constant window taps of the long-block mirror: k1 = lane (< 30)
+    float w4[4];
+    {
+        const int k1 = lane < 30 ? lane : 29;
+        w4[0] = tb.window[59 - 2 * k1];
+        w4[1] = tb.window[60 + 2 * k1];
+        w4[2] = tb.window[58 - 2 * k1];
+        w4[3] = tb.window[61 + 2 * k1];
+    }
+
+    const long long total_warps = (long long)gridDim.x * kWarpsPerCta;
+    const long long nitems = p.nruns * p.npairs;
+    uint32_t phase = 0;
+    for (long long item = (long long)blockIdx.x * kWarpsPerCta + warp; item < nitems; item += total_warps) {
+        const long long run = kStereo ? item : item / p.npairs;
+        const int pair = kStereo ? 0 : int(item - run * p.npairs);
+        const int cb = 2 * pair;
+        const int nch = kStereo ? 2 : (p.C - cb >= 2 ? 2 : 1);
+        const long long f0 = run * p.frames_per_run;
+        const long long f1 = (f0 + p.frames_per_run < p.nframes) ? f0 + p.frames_per_run : p.nframes;
+        // A run that does not open the batch (or a batch with a halo frame)
+        // first re-computes the frame before it, only to obtain its raw tail.
+        const bool warm = f0 > 0 || p.halo_coef != nullptr;
+        for (int i = lane; i < 2 * kHalfOvl; i += 32) {
+            const int ch = i / kHalfOvl;
+            float t = 0.f;
+            if (!warm && p.tail_in != nullptr && ch < nch) t = p.tail_in[(cb + ch) * kHalfOvl + (i - ch * kHalfOvl)];
+            ws.tail[i] = t;
+        }
+        __syncwarp();
+        long long f = warm ? f0 - 1 : f0;
+        const uint8_t *flags = p.transient + (p.flag_per_pair ? pair : 0);
+        if (lane == 0) {
+            mbar_expect_tx(&ws.bar, nch * kFrame * 4);
+            for (int ch = 0; ch < nch; ch++) {
+                const float *src = (f < 0 ? p.halo_coef : p.coef + f * p.C * kFrame) + (cb + ch) * kFrame;
+                tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
+            }
+        }
+        int is_tr = f < 0 ? p.halo_transient : flags[f * p.flag_stride];
+        for (; f < f1; f++) {
+            const bool more = f + 1 < f1;
+            const int next_tr = more ? flags[(f + 1) * p.flag_stride] : 0;
+            while (!mbar_try_wait(&ws.bar, phase)) {}
+            phase ^= 1;
+            if (!is_tr) long_frame<kStereo>(p, tb, ws, lane, f, cb, nch, f >= f0, more, f + 1, w4);
+            else short_frame<kStereo>(p, tb, ws, lane, f, cb, nch, f >= f0, more, f + 1);
+            is_tr = next_tr;
+        }
+        __syncwarp();
+        if (f1 == p.nframes && p.tail_out != nullptr) {
+            for (int i = lane; i < 2 * kHalfOvl; i += 32) {
+                const int ch = i / kHalfOvl;
+                if (ch < nch) p.tail_out[(cb + ch) * kHalfOvl + (i - ch * kHalfOvl)] = ws.tail[i];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t prepare_kernels()
+{
+    cudaError_t e = cudaFuncSetAttribute(celt_synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)fast_kernel_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(celt_synth_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)fast_kernel_smem_bytes());
+}
+
+cudaError_t launch_synth(const SynthParams &p, int num_sms, cudaStream_t stream, int *launched_ctas)
+{
+    const long long nitems = p.nruns * p.npairs;
+    long long ctas = (nitems + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (ctas > num_sms) ctas = num_sms;   // persistent: one CTA per SM, warps stride over the items
+    if (ctas < 1) ctas = 1;
+    if (launched_ctas) *launched_ctas = (int)ctas;
+    const size_t smem = fast_kernel_smem_bytes();
+    if (p.C == 2)
+        celt_synth_kernel<true><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+    else
+        celt_synth_kernel<false><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------- generic kernel ---
+// One clt_mdct_backward call per CTA for ANY (shift, stride): the drop-in
+// entry points (single calls, all four transform sizes) and the LM < 3
+// shapes.  Follows the reference formulas literally for the rotations
+// (mdct.c:295-313, :320-359, :361-377) with the reference's trig/window
+// tables; the N4-point inverse DFT is 30 x R (R = 16, 8, 4, 2): 30-point
+// prime-factor DFTs in registers, then an R-term direct sum.  Latency-bound
+// by design (a batch of one); throughput work belongs to the fast kernel.
+constexpr int kGenericThreads = 128;
+
+__global__ void __launch_bounds__(kGenericThreads) mdct_backward_generic_kernel(const MdctCall *calls, const GenericTables *tabs)
+{
+    __shared__ float2 a_buf[480];   // pre-rotated input, later the FFT output
+    __shared__ float2 b_buf[480];   // stage-1 output, later y[] as 960 floats
+    __shared__ float s_trig[481];
+    __shared__ float s_win[kOverlap];
+
+    const MdctCall call = calls[blockIdx.x];
+    const int shift = call.shift, stride = call.stride;
+    const int N = kMdctN >> shift, N2 = N >> 1, N4 = N >> 2, R = N4 / 30;
+    const float sine = (float)2 * 3.141592653f * (.125f) / N;   // mdct.c:292
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < 481; i += kGenericThreads) s_trig[i] = tabs->trig[i];
+    for (int i = tid; i < kOverlap; i += kGenericThreads) s_win[i] = tabs->window[i];
+    __syncthreads();
+
+    // pre-rotate, mdct.c:303-312
+    for (int i = tid; i < N4; i += kGenericThreads) {
+        if (call.ifft_only) {
+            a_buf[i] = reinterpret_cast<const float2 *>(call.in)[i];
+            continue;
+        }
+        const float x1 = call.in[(size_t)2 * i * stride];
+        const float x2 = call.in[(size_t)(N2 - 1 - 2 * i) * stride];
+        const float t0 = s_trig[i << shift], t1 = s_trig[(N4 - i) << shift];
+        const float yr = -(x2 * t0) + x1 * t1;
+        const float yi = -(x2 * t1) - x1 * t0;
+        a_buf[i] = make_float2(yr - yi * sine, yi + yr * sine);
+    }
+    __syncthreads();
+
+    // inverse DFT, N4 = 30 * R: i = R*n1 + n2, k = k1 + 30*k2
+    if (tid < R) {
+        const int n2 = tid;
+        float2 g[30];
+#pragma unroll
+        for (int n1 = 0; n1 < 30; n1++) g[n1] = a_buf[R * n1 + n2];
+        idft30(g);
+#pragma unroll
+        for (int k1 = 0; k1 < 30; k1++) {
+            float sn, cs;
+            sincospif(2.0f * (float)(n2 * k1) / (float)N4, &sn, &cs);   // exp(+j 2pi n2 k1 / N4)
+            b_buf[n2 * 30 + k1] = cmulc(g[k1], cs, sn);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < N4; k += kGenericThreads) {
+        const int k1 = k % 30, k2 = k / 30;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int n2 = 0; n2 < R; n2++) {
+            float sn, cs;
+            sincospif(2.0f * (float)((n2 * k2) % R) / (float)R, &sn, &cs);
+            acc = cadd(acc, cmulc(b_buf[n2 * 30 + k1], cs, sn));
+        }
+        a_buf[k] = acc;
+        if (call.ifft_only) reinterpret_cast<float2 *>(call.out)[k] = acc;
+    }
+    if (call.ifft_only) return;
+    __syncthreads();
+
+    // post-rotate + de-shuffle, mdct.c:330-358: bin k -> y[2k], y[N2-1-2k]
+    float *y = reinterpret_cast<float *>(b_buf);
+    for (int k = tid; k < N4; k += kGenericThreads) {
+        const float re = a_buf[k].x, im = a_buf[k].y;
+        const float t0 = s_trig[k << shift], t1 = s_trig[(N4 - k) << shift];
+        const float yr = re * t0 - im * t1;
+        const float yi = im * t0 + re * t1;
+        y[2 * k] = -(yr - yi * sine);
+        y[N2 - 1 - 2 * k] = yi + yr * sine;
+    }
+    __syncthreads();
+
+    // out[60+m] = y[m]; TDAC mirror on out[0..120) with the previous tail, mdct.c:368-376
+    for (int m = kHalfOvl + tid; m < N2; m += kGenericThreads) call.out[kHalfOvl + m] = y[m];
+    for (int i = tid; i < kHalfOvl; i += kGenericThreads) {
+        const float x1 = y[kHalfOvl - 1 - i];   // out[119 - i]
+        const float x2 = call.out[i];
+        call.out[i] = s_win[kOverlap - 1 - i] * x2 - s_win[i] * x1;
+        call.out[kOverlap - 1 - i] = s_win[i] * x2 + s_win[kOverlap - 1 - i] * x1;
+    }
+}
+
+cudaError_t launch_mdct_generic(const MdctCall *d_calls, int ncalls, const GenericTables *d_tables, cudaStream_t stream)
+{
+    if (ncalls <= 0) return cudaSuccess;
+    mdct_backward_generic_kernel<<<ncalls, kGenericThreads, 0, stream>>>(d_calls, d_tables);
+    return cudaGetLastError();
+}
+
+}  // namespace nq

@@ -1,0 +1,68 @@
+// Shared declarations between the kernels (celt_synth_kernels.cu) and the
+// host layer / C-ABI (celt_synth_api.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nq {
+
+constexpr int kFrame = 960;      // samples per channel per 20 ms frame (N2 of the long MDCT)
+constexpr int kHalfOvl = 60;     // overlap/2: raw tail carried between (sub-)blocks
+constexpr int kOverlap = 120;    // mode->overlap, static_modes_float.h:579
+constexpr int kMdctN = 1920;     // mode->mdct.n,  static_modes_float.h:591
+
+// Fast kernel geometry: one warp owns one run of consecutive frames of one
+// channel pair; warps are independent (no block-wide barrier in the loop).
+constexpr int kWarpsPerCta = 14;
+constexpr int kInRowFloats = 968;        // 960 coefficients + 8 pad (bank offset between the two rows)
+constexpr int kXRowF2 = 31;              // padded row of the 16x30 inter-stage buffer (float2 units)
+constexpr int kXChanF2 = 16 * kXRowF2;   // 496 float2 per channel
+
+// Tables the fast kernel keeps in shared memory (one copy per CTA).  Built on
+// the host in double precision by build_tables() (celt_synth_api.cu).
+struct FastTables {
+    float2 t_long[kXChanF2];   // [n2][k1] (row stride 31): -(1+js)^2 e^{j2pi(n2+k1)/1920} e^{j2pi n2 k1/480}
+    float2 t_short[2 * 30];    // [h][k1]:                  -(1+js)^2 e^{j2pi(h+k1)/240}  e^{j2pi h k1/60}
+    float window[kOverlap];    // static_modes_float.h:9 window120 (modes.c:374 formula)
+};
+
+// Tables of the generic (any shift / stride) kernel: the reference's own
+// trig + window tables (mdct.c:99, modes.c:374).
+struct GenericTables {
+    float trig[481];
+    float window[kOverlap];
+};
+
+struct SynthParams {
+    const float *coef;          // [nframes][C][960]
+    const uint8_t *transient;   // [nframes][flag_stride]
+    const float *tail_in;       // [C][60] or nullptr
+    const float *halo_coef;     // [C][960] coefficients of frame -1, or nullptr
+    float *pcm;                 // [nframes*960][C]
+    float *tail_out;            // [C][60] or nullptr
+    const FastTables *tables;
+    long long nframes;
+    long long frames_per_run;
+    long long nruns;
+    int C;
+    int npairs;
+    int halo_transient;
+    int flag_stride;            // bytes between the flags of consecutive frames
+    int flag_per_pair;          // 0: every channel pair reads column 0; 1: pair p reads column p
+};
+
+// One clt_mdct_backward call (mdct.c:267): device pointers.
+struct MdctCall {
+    const float *in;   // N2 coefficients at `stride`
+    float *out;        // N2 + 60 floats, [0,60) read (previous raw tail), all written
+    int shift;
+    int stride;
+    int ifft_only;     // 1: `in`/`out` are N4 interleaved complex values; only opus_ifft (kiss_fft.c:696) is run
+};
+
+size_t fast_kernel_smem_bytes();
+cudaError_t launch_synth(const SynthParams &p, int num_sms, cudaStream_t stream, int *launched_ctas);
+cudaError_t launch_mdct_generic(const MdctCall *d_calls, int ncalls, const GenericTables *d_tables, cudaStream_t stream);
+cudaError_t prepare_kernels();
+
+}  // namespace nq

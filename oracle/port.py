@@ -114,3 +114,12 @@ def synth_batch(coef, transient, tail_in=None, nthreads=1, want_pcm=True):
     sec = lib().nqo_synth_batch(_fp(coef), tr.ctypes.data_as(C.c_void_p), _fp(ti),
                                 _fp(pcm), _fp(tail), nframes, Cn, int(nthreads))
     return pcm, tail, sec
+
+
+def compute_inv_mdcts(shortBlocks: int, X: np.ndarray, out_mem, Cn: int, LM: int) -> None:
+    """celt_decoder_clean.c:264 on caller buffers: X [C][N*B], out_mem = list of C
+    float32 arrays (>= N*B+60), [0,60) = previous raw tail on entry."""
+    X = np.ascontiguousarray(X, np.float32)
+    fp = C.POINTER(C.c_float)
+    outs = (fp * Cn)(*[_fp(o) for o in out_mem])
+    lib().nqo_compute_inv_mdcts(int(shortBlocks), _fp(X), outs, int(Cn), int(LM))

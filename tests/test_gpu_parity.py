@@ -1,0 +1,252 @@
+"""GPU parity tests (-m gpu): every call goes through the C ABI
+(include/nq_celt_synth.h) of the CUDA library and is compared with the CPU
+oracle / the compiled-reference fixtures.
+
+Bar (BASELINE.json north_star): max |gpu - reference| <= 1e-5 * 32768 and
+SNR >= 100 dB -- float32 path, FFT factorisation differs from kiss_fft's, so
+tolerance-based, never bit-exact (conftest.assert_parity).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, FULL_SCALE, TOL_FS, assert_parity, load_npz, snr_db
+import libnyquist_b200 as nq
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def synth():
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    with nq.CeltSynth(0) as s:
+        yield s
+
+
+def case_names(z):
+    return sorted({k.split(".")[0] for k in z.files})
+
+
+def rand_batch(rng, nframes, C, p_transient=0.05, amp=1000.0):
+    k = np.arange(960)
+    env = amp / (1.0 + k / 60.0)
+    coef = (rng.uniform(-1, 1, (nframes, C, 960)) * env).astype(np.float32)
+    coef[..., 800:] = 0
+    tr = (rng.uniform(size=nframes) < p_transient).astype(np.uint8)
+    return coef, tr
+
+
+# ---- a3.2 opus_ifft against the reference's own golden vectors --------------
+@pytest.mark.parametrize("n,shift", [(480, 0), (60, 3)])
+def test_opus_ifft_reference_golden_vectors(synth, n, shift):
+    x = np.fromfile(os.path.join(GOLDEN, f"ifft_input_N{n}.bin"), np.float32)
+    y = np.fromfile(os.path.join(GOLDEN, f"ifft_output_N{n}.bin"), np.float32)
+    got = synth.opus_ifft(x, shift)
+    # same relative bar as the time-domain one: 1e-5 of the vector's own full scale
+    assert np.abs(got - y).max() <= 1e-5 * np.abs(y).max()
+    assert snr_db(y, got) >= 100.0
+
+
+@pytest.mark.parametrize("shift", [0, 1, 2, 3])
+def test_opus_ifft_batch_vs_oracle(synth, shift):
+    rng = np.random.default_rng(shift)
+    n = 2 * (480 >> shift)
+    x = (rng.standard_normal((17, n)) * 1000).astype(np.float32)
+    got = synth.opus_ifft(x, shift)
+    want = np.stack([port.opus_ifft(r, shift) for r in x])
+    assert_parity(want, got, f"ifft shift {shift}")
+
+
+# ---- a3 clt_mdct_backward, all shifts and strides --------------------------
+def test_clt_mdct_backward_all_shifts_and_strides():
+    z = load_npz("mdct_calls.npz")
+    for shift in range(4):
+        for stride in (1, 2, 4, 8):
+            key = f"s{shift}_st{stride}"
+            inp = z[key + ".in"].copy()
+            out = z[key + ".out_before"].copy()
+            nq.clt_mdct_backward(inp, out, shift, stride)
+            assert np.array_equal(inp, z[key + ".in"]), "input must be left untouched"
+            assert_parity(z[key + ".out_after"], out, key)
+
+
+def test_clt_mdct_backward_B1_C2_and_fork_seam():
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    L = nq.load_library()
+    for shift, stride in ((0, 1), (3, 8)):
+        N2 = 960 >> shift
+        ins = [(rng.standard_normal(N2 * stride) * 900).astype(np.float32) for _ in range(2)]
+        outs0 = [(rng.standard_normal(N2 + 60) * 300).astype(np.float32) for _ in range(2)]
+        want = [o.copy() for o in outs0]
+        for c in range(2):
+            port.clt_mdct_backward(ins[c], want[c], shift, stride)
+        got = [o.copy() for o in outs0]
+        nq.clt_mdct_backward_B1_C2(ins, got, shift, stride)
+        for c in range(2):
+            assert_parity(want[c], got[c], f"B1_C2 shift {shift} ch {c}")
+        # the fork's seam, cuda/mdct_cuda.hpp:92-98 (N, sine, trig, window passed as mdct.c:223-243 does)
+        got2 = [o.copy() for o in outs0]
+        fp = C.POINTER(C.c_float)
+        pin = (fp * 2)(*[a.ctypes.data_as(fp) for a in ins])
+        pout = (fp * 2)(*[a.ctypes.data_as(fp) for a in got2])
+        N = 1920 >> shift
+        sine = float(np.float32(2) * np.float32(3.141592653) * np.float32(.125) / np.float32(N))
+        L.processMDCTCudaB1C2(pin, pout, None, N, shift, stride, sine, 120, None)
+        for c in range(2):
+            assert np.array_equal(got2[c], got[c])
+        got3 = outs0[0].copy()
+        L.processMDCTCuda(ins[0].ctypes.data_as(fp), got3.ctypes.data_as(fp), None, N, shift, stride, sine, 120, None)
+        assert np.array_equal(got3, got[0])
+    L.cleanupCudaBuffers()
+    L.printCudaVersion()
+
+
+# ---- a1 compute_inv_mdcts, every LM / shortBlocks / C combination ------------
+@pytest.mark.parametrize("LM", [0, 1, 2, 3])
+@pytest.mark.parametrize("short", [False, True])
+@pytest.mark.parametrize("C", [1, 2])
+def test_compute_inv_mdcts_all_shapes(synth, LM, short, C):
+    rng = np.random.default_rng(100 * LM + 10 * short + C)
+    M = 1 << LM
+    N = 120 * M
+    X = (rng.standard_normal((C, N)) * 700).astype(np.float32)
+    outs0 = [(rng.standard_normal(N + 60) * 200).astype(np.float32) for _ in range(C)]
+    want = [o.copy() for o in outs0]
+    port.compute_inv_mdcts(M if short else 0, X, want, C, LM)
+    got = [o.copy() for o in outs0]
+    synth.compute_inv_mdcts(M if short else 0, X, got, C, LM)
+    for c in range(C):
+        assert_parity(want[c], got[c], f"LM {LM} short {short} C {C} ch {c}")
+
+
+# ---- batched phase 2 against compiled-reference fixtures ---------------------
+@pytest.mark.parametrize("name", case_names(load_npz("synth_cases.npz")))
+def test_synth_batch_vs_compiled_reference_fixture(synth, name):
+    z = load_npz("synth_cases.npz")
+    tail_in = z[name + ".tail_in"]
+    tail_in = None if tail_in.size == 0 else tail_in
+    pcm, tail = synth.synth_batch(z[name + ".coef"], z[name + ".transient"], tail_in)
+    assert_parity(z[name + ".pcm"], pcm, name)
+    assert_parity(z[name + ".tail_out"], tail, name + " tail")
+
+
+@pytest.mark.parametrize("tag", ["reverie", "reverie60", "short"])
+def test_real_frames_recorded_from_bundled_opus_files(synth, tag):
+    """BASELINE configs 1-3: coefficients recorded while the reference decoded
+    sb-reverie.opus / sb-reverie-60ms-frames.opus / short.opus (incl. transients)."""
+    z = load_npz("real_frames.npz")
+    coef, tr, out = z[tag + ".coef"], z[tag + ".transient"], z[tag + ".out"]
+    pcm, _ = synth.synth_batch(np.ascontiguousarray(coef), tr, None)
+    pcm = pcm.reshape(coef.shape[0], 960, 2).transpose(0, 2, 1)
+    assert_parity(out[1:], pcm[1:], tag)
+
+
+@pytest.mark.parametrize("C", [1, 2, 3, 8])
+@pytest.mark.parametrize("p_tr", [0.0, 0.05, 1.0])
+def test_synth_batch_many_runs_vs_oracle(synth, C, p_tr):
+    """Enough frames for thousands of warp runs: exercises the run-boundary re-synthesis."""
+    rng = np.random.default_rng(1000 + C)
+    nframes = 5000 if C <= 2 else 1500
+    coef, tr = rand_batch(rng, nframes, C, p_tr)
+    tail_in = (rng.standard_normal((C, 60)) * 100).astype(np.float32)
+    want, want_tail, _ = port.synth_batch(coef, tr, tail_in, nthreads=8)
+    pcm, tail = synth.synth_batch(coef, tr, tail_in)
+    assert_parity(want, pcm, f"C {C} p {p_tr}")
+    assert_parity(want_tail, tail, "tail")
+
+
+def test_edge_cases_and_error_codes(synth):
+    rng = np.random.default_rng(5)
+    # empty batch: tail passes through
+    tail_in = rng.standard_normal((2, 60)).astype(np.float32)
+    pcm, tail = synth.synth_batch(np.zeros((0, 2, 960), np.float32), np.zeros(0, np.uint8), tail_in)
+    assert pcm.shape == (0, 2) and np.array_equal(tail, tail_in)
+    # zero coefficients, zero tail -> exact zeros
+    pcm, tail = synth.synth_batch(np.zeros((9, 2, 960), np.float32), np.array([0, 1] * 4 + [0], np.uint8))
+    assert not pcm.any() and not tail.any()
+    # bad arguments are refused, not crashed on
+    L = nq.load_library()
+    assert L.nq_celt_synth_batch_host(synth._h, None, None, None, None, None, 4, 2) == -1
+    assert L.nq_celt_synth_batch_host(synth._h, None, None, None, None, None, 4, 0) == -1
+    assert L.nq_celt_synth_batch_host(synth._h, None, None, None, None, None, -1, 2) == -1
+    assert L.nq_compute_inv_mdcts(synth._h, 3, None, None, 2, 3) == -1
+    with pytest.raises(nq.NqError):
+        synth.compute_inv_mdcts(4, np.zeros((2, 960), np.float32), [np.zeros(1020, np.float32)] * 2, 2, 3)
+
+
+# ---- device-pointer entry (what bench.py times) -----------------------------
+def test_device_entry_tail_and_halo_and_chaining(synth):
+    import torch
+    rng = np.random.default_rng(21)
+    nframes, C = 4000, 2
+    coef, tr = rand_batch(rng, nframes, C, 0.1)
+    want, want_tail, _ = port.synth_batch(coef, tr, None, nthreads=8)
+    d_coef = torch.from_numpy(coef).cuda()
+    d_tr = torch.from_numpy(tr).cuda()
+    pcm, tail = synth.synth_batch_torch(d_coef, d_tr)
+    torch.cuda.synchronize()
+    assert_parity(want, pcm.cpu().numpy(), "device whole")
+    assert_parity(want_tail, tail.cpu().numpy(), "device tail")
+    # two calls chained through tail_out -> tail_in must equal one call BIT FOR BIT
+    cut = 1777
+    a, ta = synth.synth_batch_torch(d_coef[:cut].contiguous(), d_tr[:cut].contiguous())
+    b, tb = synth.synth_batch_torch(d_coef[cut:].contiguous(), d_tr[cut:].contiguous(), tail_in=ta)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([a, b]), pcm) and torch.equal(tb, tail)
+    # the same second half from a halo frame instead of a tail (multi-GPU shard start)
+    b2, _ = synth.synth_batch_torch(d_coef[cut:].contiguous(), d_tr[cut:].contiguous(),
+                                    halo_coef=d_coef[cut - 1].contiguous(), halo_transient=int(tr[cut - 1]))
+    torch.cuda.synchronize()
+    assert torch.equal(b2, b)
+
+
+def test_full_size_properties_on_device(synth):
+    """Size-independent checks at a large batch (1M stereo frames, 15 GB of traffic):
+    exact homogeneity under power-of-two scaling, shard invariance, and spot
+    parity of randomly chosen frames against the oracle."""
+    import torch
+    nframes, C = 1_000_000, 2
+    g = torch.Generator(device="cuda").manual_seed(0x0B200)
+    env = (1000.0 / (1.0 + torch.arange(960, device="cuda") / 60.0)).float()
+    env[800:] = 0
+    coef = (torch.rand((nframes, C, 960), generator=g, device="cuda") * 2 - 1) * env
+    tr = (torch.rand(nframes, generator=g, device="cuda") < 0.028).to(torch.uint8)
+    pcm, tail = synth.synth_batch_torch(coef, tr)
+    pcm2, tail2 = synth.synth_batch_torch(coef * 4.0, tr)
+    torch.cuda.synchronize()
+    assert torch.isfinite(pcm).all()
+    assert torch.equal(pcm2, pcm * 4.0) and torch.equal(tail2, tail * 4.0)
+    # spot parity: 48 random windows of 3 frames, each synthesised by the oracle from its halo
+    rng = np.random.default_rng(9)
+    worst = 0.0
+    for f in rng.integers(1, nframes - 3, 48):
+        f = int(f)
+        c = coef[f - 1:f + 3].cpu().numpy()
+        t = tr[f - 1:f + 3].cpu().numpy()
+        want, _, _ = port.synth_batch(c, t, None)
+        got = pcm[f * 960:(f + 3) * 960].cpu().numpy()
+        assert_parity(want[960:], got, f"frame {f}")
+        worst = max(worst, float(np.abs(want[960:] - got).max()))
+    print(f"worst spot error {worst / FULL_SCALE:.3e} of full scale")
+    # shard invariance across 8 contiguous shards with halos (the multi-GPU decomposition)
+    for s in nq.shard_plan(nframes, 8)[1:3]:
+        part, _ = synth.synth_batch_torch(coef[s.f0:s.f1], tr[s.f0:s.f1], halo_coef=coef[s.halo],
+                                          halo_transient=int(tr[s.halo]))
+        torch.cuda.synchronize()
+        assert torch.equal(part, pcm[s.f0 * 960:s.f1 * 960])
+
+
+def test_multi_gpu_in_process_entry(synth):
+    import torch
+    rng = np.random.default_rng(33)
+    coef, tr = rand_batch(rng, 3000, 2, 0.05)
+    tail_in = (rng.standard_normal((2, 60)) * 100).astype(np.float32)
+    want, want_tail = synth.synth_batch(coef, tr, tail_in)
+    ndev = torch.cuda.device_count()
+    for devices in ([0], list(range(ndev)), [0] * 3):
+        pcm, tail = nq.synth_batch_multi_gpu(coef, tr, tail_in, devices)
+        assert np.array_equal(pcm, want) and np.array_equal(tail, want_tail), devices

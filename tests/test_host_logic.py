@@ -1,0 +1,123 @@
+"""CPU tests of everything in the product that does not need a GPU: the C-ABI
+library loads and exports every symbol of include/nq_celt_synth.h, the
+host-built tables, the kernel design (lane-accurate model vs the oracle), the
+in-register DFT codelets (run on the host), and the shard planner."""
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_parity, load_npz
+import libnyquist_b200 as nq
+from oracle import port
+from kernel_model import WarpModel
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    nq.build_library()
+    L = nq.load_library()
+    hdr = open(os.path.join(ROOT, "include", "nq_celt_synth.h")).read()
+    declared = set(re.findall(r"^NQ_API[^;(]*?\b(\w+)\s*\(", hdr, re.M))
+    assert declared, "no NQ_API declarations found"
+    assert declared == set(nq.EXPORTED_SYMBOLS), declared ^ set(nq.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", nq.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert declared <= exported
+
+
+def test_library_contains_only_sm_100a_code_and_uses_tma():
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    nq.build_library()
+    elf = subprocess.run(["cuobjdump", "-lelf", nq.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and not re.search(r"sm_(?!100a)\d+", elf), elf
+    sass = subprocess.run(["cuobjdump", "-sass", nq.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass, "fast kernel should stage coefficient rows with TMA bulk copies"
+    assert "SHFL" in sass and "SYNCS" in sass
+
+
+def test_no_compute_without_gpu_is_loud():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(nq.NqError):
+        nq.CeltSynth(0)
+
+
+def test_host_tables_match_reference_formulas():
+    t = nq.debug_tables()
+    ref = load_npz("ref_tables.npz")
+    # window / trig are regenerated from the reference's formulas (modes.c:374, mdct.c:99);
+    # the reference ships 8-digit literals, so allow one float32 ulp.
+    assert np.abs(t["window"].astype(np.float64) - ref["window120"]).max() <= 6e-8
+    assert np.abs(t["trig"].astype(np.float64) - ref["trig481"]).max() <= 6e-8
+    assert np.array_equal(t["window"], port.tables()["window120"]) or \
+        np.abs(t["window"] - port.tables()["window120"]).max() <= 6e-8
+    tl = t["t_long"][..., 0] + 1j * t["t_long"][..., 1]
+    assert np.all(np.abs(np.abs(tl[:, :30]) - 1) < 1e-6)     # unit rotations times (1+s^2) ~ 1 + 1.7e-7
+    ts = t["t_short"][..., 0] + 1j * t["t_short"][..., 1]
+    s = float(np.float32(2) * np.float32(3.141592653) * np.float32(.125) / np.float32(240))
+    assert np.allclose(np.abs(ts), 1 + s * s, atol=2e-7)      # the reference's sin(x)~x gain, SURVEY.md 3.3
+
+
+@pytest.mark.parametrize("name", ["stereo_long", "stereo_short", "stereo_mixed_tail", "mono_mixed_tail",
+                                  "three_ch_mixed", "single_frame_long", "single_frame_short"])
+def test_kernel_design_model_matches_reference_fixtures(name):
+    z = load_npz("synth_cases.npz")
+    model = WarpModel(nq.debug_tables())
+    tail_in = z[name + ".tail_in"]
+    tail_in = None if tail_in.size == 0 else tail_in
+    pcm, tail = model.synth(z[name + ".coef"].astype(np.float64), z[name + ".transient"], tail_in)
+    assert_parity(z[name + ".pcm"], pcm, name)
+    assert_parity(z[name + ".tail_out"], tail, name + " tail")
+
+
+def test_codelets_on_host():
+    nvcc = shutil.which("nvcc")
+    if nvcc is None:
+        pytest.skip("nvcc not on PATH")
+    exe = "/tmp/nq_host_codelet_check"
+    subprocess.run([nvcc, "-O2", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(ROOT, "tests", "host_codelet_check.cu")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_shard_plan_is_a_partition_with_one_frame_halos():
+    for nframes in (0, 1, 7, 8, 1000, 10_000_000):
+        for world in (1, 2, 3, 4, 8):
+            plan = nq.shard_plan(nframes, world)
+            assert plan[0].f0 == 0 and plan[-1].f1 == nframes
+            for a, b in zip(plan, plan[1:]):
+                assert a.f1 == b.f0
+            sizes = [s.nframes for s in plan]
+            assert max(sizes) - min(sizes) <= 1
+            for s in plan:
+                assert s.halo == (s.f0 - 1 if s.f0 > 0 and s.nframes > 0 else None)
+
+
+def test_sharded_synthesis_equals_unsharded_oracle():
+    """Shard + halo + gather reproduces the unsharded result (oracle as stand-in compute)."""
+    rng = np.random.default_rng(3)
+    nframes, C = 23, 2
+    coef = (rng.standard_normal((nframes, C, 960)) * 500).astype(np.float32)
+    tr = (rng.uniform(size=nframes) < 0.4).astype(np.uint8)
+    tail_in = (rng.standard_normal((C, 60)) * 50).astype(np.float32)
+    want, want_tail, _ = port.synth_batch(coef, tr, tail_in)
+    for world in (2, 3, 5):
+        parts = []
+        tail = None
+        for s in nq.shard_plan(nframes, world):
+            if s.halo is None:
+                pcm, tail, _ = port.synth_batch(coef[s.f0:s.f1], tr[s.f0:s.f1], tail_in)
+            else:   # re-synthesise the halo frame only for its tail
+                _, halo_tail, _ = port.synth_batch(coef[s.halo:s.halo + 1], tr[s.halo:s.halo + 1], None)
+                pcm, tail, _ = port.synth_batch(coef[s.f0:s.f1], tr[s.f0:s.f1], halo_tail)
+            parts.append(pcm)
+        got = np.concatenate(parts)
+        assert np.array_equal(got, want) and np.array_equal(tail, want_tail)
