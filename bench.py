@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the CELT synthesis hot path (inverse MDCT + TDAC overlap-add +
+stereo interleave) on B200, metric and workload as BASELINE.json names them.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl reference]
+
+One step = one pass of the hot path over one batch of synthetic stereo 20 ms
+CELT frames (BASELINE.json configs[4]: 10 M frames; coefficients uniform with
+a band-decaying envelope, zero above bin 800, 2.8 % transient frames).  At
+N > 1 (launched under torchrun, one rank per GPU) every rank owns its own
+contiguous frame range of the same size (weak scaling, no data-path
+collective: each shard only needs the previous frame as a halo).
+
+Prints ONE JSON line:
+  value      whole-job frames/s with the inputs resident in HBM (CUDA events
+             on the launching stream, max over ranks)
+  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D of
+             the coefficients, kernel, D2H of the PCM inside the timed region
+  roofline   achieved algorithmic GB/s (15 360 B per stereo frame) of the
+             dominant kernel vs the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own compute_inv_mdcts (oracle/_ref, else the
+             C oracle port) on the box's host cores, bounded sample
+--impl reference times that CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_FRAME = 2 * 960 * 4 * 2          # stereo: 7680 B read + 7680 B written
+METRIC = "celt_imdct_ola_frames_per_s"
+UNIT = "frames/s"
+DEFAULT_FRAMES = 10_000_000               # BASELINE.json configs[4]
+P_TRANSIENT = 0.028                       # measured frame mix of sb-reverie.opus
+E2E_FRAMES = 262_144                      # host-buffer leg: 2 GB in + 2 GB out of pinned memory per step
+FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of celt_synth_kernel<true> from the
+# committed ncu capture (profiles/), scaled to bytes per frame; None until a capture exists.
+NCU_TRAFFIC_BYTES_PER_FRAME = None
+
+
+def workload_name(frames):
+    return (f"synthetic batch of {frames} stereo 20 ms CELT frames per GPU (2x960 f32 coefficients -> 2x960 f32 "
+            f"samples, {P_TRANSIENT * 100:.1f}% transient), BASELINE.json configs[4]")
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML, 20 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------ CPU arm ---
+def cpu_reference_run(frames_per_pass, passes, steps, warmup):
+    """The reference's compute_inv_mdcts over stereo frames on all host cores.
+    Returns (frames/s, cores, kind, sample description, ms per step)."""
+    import numpy as np
+    from oracle import port, ref
+    use_ref = ref.available()
+    mod = ref if use_ref else port
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0x0B200)
+    env = (1000.0 / (1.0 + np.arange(960) / 60.0)).astype(np.float32)
+    env[800:] = 0
+    coef = rng.uniform(-1, 1, (frames_per_pass, 2, 960)).astype(np.float32) * env
+    tr = (rng.uniform(size=frames_per_pass) < P_TRANSIENT).astype(np.uint8)
+    best = None
+    times = []
+    for it in range(warmup + steps):
+        t = 0.0
+        for _ in range(passes):
+            _, _, sec = mod.synth_batch(coef, tr, None, nthreads=cores)
+            t += sec
+        if it >= warmup:
+            times.append(t)
+            best = t if best is None else min(best, t)
+    mean = sum(times) / len(times)
+    kind = "reference" if use_ref else "port"
+    sample = (f"{passes} x {frames_per_pass} stereo frames per step on {cores} threads "
+              f"({'oracle/_ref: reference sources compiled in place' if use_ref else 'oracle/ C restatement'}; "
+              f"gcc -O3, contiguous frame ranges per thread)")
+    return frames_per_pass * passes / mean, cores, kind, sample, mean * 1e3
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    value, cores, kind, sample, ms = cpu_reference_run(65536, 2, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.frames), "note": "CPU arm: bounded sample of the same workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------ GPU arm ---
+def make_device_batch(torch, frames, device, seed):
+    """Coefficients generated on the device chunk by chunk (no host copy of 77 GB)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    env = (1000.0 / (1.0 + torch.arange(960, device=device) / 60.0)).float()
+    env[800:] = 0
+    coef = torch.empty((frames, 2, 960), dtype=torch.float32, device=device)
+    step = 262_144
+    for f0 in range(0, frames, step):
+        v = coef[f0:f0 + step]
+        v.uniform_(-1.0, 1.0, generator=g)
+        v.mul_(env)
+    tr = (torch.rand(frames, generator=g, device=device) < P_TRANSIENT).to(torch.uint8)
+    return coef, tr
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=DEFAULT_FRAMES, help="stereo frames per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import libnyquist_b200 as nq
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libnyquist_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)   # plumbing only: barriers + max-over-ranks of the times
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    synth = nq.CeltSynth(local)
+    frames = args.frames
+    # Resident workload: the whole batch in HBM (10 M frames = 76.8 GB in + 76.8 GB out).  If it does
+    # not fit, halve until it does and say so -- never silently.
+    free, _total = torch.cuda.mem_get_info()
+    resident_note = "whole batch resident in HBM"
+    while frames * BYTES_PER_FRAME + (6 << 30) > free and frames > 1024:
+        frames //= 2
+        resident_note = f"batch reduced to {frames} frames to fit {free >> 30} GiB free HBM"
+    coef, tr = make_device_batch(torch, frames, dev, 0x0B200 + rank)
+    pcm = torch.empty((frames * 960, 2), dtype=torch.float32, device=dev)
+    # every rank but the first starts mid-stream: hand it a halo frame like a real shard gets
+    halo = coef[frames // 2].clone() if rank > 0 else None
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        synth.synth_batch_torch(coef, tr, halo_coef=halo, halo_transient=0, out=pcm, want_tail=False, stream=stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = synth.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local) as clocks:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step()
+            ev[i + 1].record(stream)
+        barrier()
+    launches = synth.launch_count - l0
+    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * frames * args.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        ef = min(E2E_FRAMES, frames)
+        h_coef = torch.empty((ef, 2, 960), dtype=torch.float32, pin_memory=True)
+        h_coef.copy_(coef[:ef])
+        h_tr = torch.empty(ef, dtype=torch.uint8, pin_memory=True)
+        h_tr.copy_(tr[:ef])
+        h_pcm = torch.empty((ef * 960, 2), dtype=torch.float32, pin_memory=True)
+        h_tail = torch.empty((2, 60), dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            synth.synth_batch_host_ptr(h_coef.data_ptr(), h_tr.data_ptr(), 0, h_pcm.data_ptr(), h_tail.data_ptr(), ef, 2)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()          # synchronous: returns when the PCM is back in host memory
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ef * args.steps / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": ef * (7680 + 1), "d2h_bytes_per_step": ef * 7680 + 480,
+               "frames_per_step": ef, "ms_per_step": float(t.item()) * 1e3 / args.steps,
+               "note": "nq_celt_synth_batch_host: pinned host buffers, chunked H2D/kernel/D2H pipeline; bounded batch"}
+        if rank == 0:
+            got = h_pcm[:960 * 4].numpy().copy()
+            assert np.isfinite(got).all()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = hbm_peak()
+    kernel_ms = sum(per_step_ms) / len(per_step_ms)          # one launch per step: this IS the kernel's launch duration
+    achieved = frames * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None if NCU_TRAFFIC_BYTES_PER_FRAME is None else NCU_TRAFFIC_BYTES_PER_FRAME * frames,
+        "kernel": "nq::celt_synth_kernel<true>", "algorithmic_bytes_per_launch": frames * BYTES_PER_FRAME,
+        "launch_ms": kernel_ms, "peak_source": peak_src,
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(frames), "frames_per_gpu": frames, "channels": 2,
+                   "residency": resident_note,
+                   "l2": "inputs (7680 B/frame x frames) far larger than the 126 MB L2; no flush needed",
+                   "hbm_gbs_aggregate": value * BYTES_PER_FRAME / 1e9},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks.summary(),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, kind, sample, _ = cpu_reference_run(65536, 2, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
