@@ -41,7 +41,7 @@ E2E_FRAMES = 262_144                      # host-buffer leg: 2 GB in + 2 GB out 
 FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of celt_synth_kernel<true> from the
 # committed ncu capture (profiles/), scaled to bytes per frame; None until a capture exists.
-NCU_TRAFFIC_BYTES_PER_FRAME = None
+NCU_TRAFFIC_BYTES_PER_FRAME = 15340.2    # profiles/r1_ncu_full_celt_synth_kernel_1Mframes.csv: (7.703919 + 7.636280) GB / 1e6 frames
 
 
 def workload_name(frames):
@@ -284,6 +284,18 @@ def main():
             got = h_pcm[:960 * 4].numpy().copy()
             assert np.isfinite(got).all()
 
+    # The timed output must be the real thing: spot-check frames of the last step against the oracle.
+    from oracle import port
+    worst = 0.0
+    for f in (1, frames // 3, frames - 2):
+        if f < 1 or f + 1 > frames:
+            continue
+        want, _, _ = port.synth_batch(coef[f - 1:f + 1].cpu().numpy(), tr[f - 1:f + 1].cpu().numpy(), None)
+        got = pcm[f * 960:(f + 1) * 960].cpu().numpy()
+        worst = max(worst, float(np.abs(got - want[960:]).max()) / 32768.0)
+    if not worst <= 1e-5:
+        raise SystemExit(f"bench.py: output of the timed step fails parity ({worst:.3e} of full scale)")
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -292,6 +304,8 @@ def main():
     peak, peak_src = hbm_peak()
     kernel_ms = sum(per_step_ms) / len(per_step_ms)          # one launch per step: this IS the kernel's launch duration
     achieved = frames * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+    if achieved > 1.3 * peak:
+        raise SystemExit(f"bench.py: {achieved:.0f} GB/s is far above the HBM peak: the timed region missed the kernel")
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None if NCU_TRAFFIC_BYTES_PER_FRAME is None else NCU_TRAFFIC_BYTES_PER_FRAME * frames,
@@ -307,6 +321,7 @@ def main():
                    "l2": "inputs (7680 B/frame x frames) far larger than the 126 MB L2; no flush needed",
                    "hbm_gbs_aggregate": value * BYTES_PER_FRAME / 1e9},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks.summary(),
+        "parity_spot_check_max_err_of_full_scale": worst,
     }
     if not args.no_cpu_baseline and world == 1:
         v, cores, kind, sample, _ = cpu_reference_run(65536, 2, 3, 1)

@@ -242,6 +242,8 @@ class CeltSynth:
         pcm = out if out is not None else torch.empty((nframes * FRAME, Cn), dtype=torch.float32, device=coef.device)
         tail = torch.empty((Cn, HALF_OVERLAP), dtype=torch.float32, device=coef.device) if want_tail else None
         st = (stream if stream is not None else torch.cuda.current_stream(coef.device)).cuda_stream
+        if st == 0:
+            st = 1   # torch's default stream is the legacy default stream: cudaStreamLegacy (NULL would mean ctx's own stream)
         self.synth_batch_device_ptr(coef.data_ptr(), transient.data_ptr(),
                                     0 if tail_in is None else tail_in.data_ptr(),
                                     0 if halo_coef is None else halo_coef.data_ptr(), halo_transient,
