@@ -35,3 +35,23 @@ def shard_range(nframes: int, world: int, rank: int) -> Shard:
 
 def shard_plan(nframes: int, world: int) -> List[Shard]:
     return [shard_range(nframes, world, r) for r in range(world)]
+
+
+def take_shard(coef, transient, world: int, rank: int):
+    """Slices one rank's work out of a whole stream held as arrays/tensors
+    indexed [frame, ...]: returns (coef_shard, transient_shard, halo_coef or
+    None, halo_transient)."""
+    s = shard_range(len(transient), world, rank)
+    halo_coef = None if s.halo is None else coef[s.halo]
+    halo_tr = 0 if s.halo is None else int(transient[s.halo])
+    return coef[s.f0:s.f1], transient[s.f0:s.f1], halo_coef, halo_tr
+
+
+def max_over_ranks(value: float, dist=None, device=None) -> float:
+    """Multi-GPU times are reported as the max over ranks (bench contract)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
