@@ -250,3 +250,44 @@ def test_multi_gpu_in_process_entry(synth):
     for devices in ([0], list(range(ndev)), [0] * 3):
         pcm, tail = nq.synth_batch_multi_gpu(coef, tr, tail_in, devices)
         assert np.array_equal(pcm, want) and np.array_equal(tail, want_tail), devices
+
+
+# ---- BASELINE configs 1-3: every frame of the bundled files -----------------
+REAL_FILES = {"sb-reverie.opus": (11184, 314), "sb-reverie-60ms-frames.opus": (11184, 298), "short.opus": (None, None)}
+
+
+@pytest.mark.parametrize("fname", sorted(REAL_FILES))
+def test_whole_bundled_file_coefficient_stream(synth, fname):
+    """Phase 1 = the reference's own decoder (oracle/_ref, compiled in place) recording freq[] at
+    the inverse-MDCT call sites; phase 2 = ONE batched GPU call over every 20 ms stereo frame of
+    the file; compared with the out_syn the reference produced for the same frames."""
+    from oracle import ref
+    path = os.path.join(os.path.dirname(ref.LIB_PATH), "test_data", fname)
+    if not (ref.available() and os.path.exists(path)):
+        pytest.skip("oracle/_ref (compiled reference + staged test_data) not present")
+    pcm_ref, recs = ref.decode_file(path, record=True)
+    # keep the maximal prefix-free set of consecutive LM=3 stereo frames (short.opus has one LM=0 frame)
+    idx = [i for i, r in enumerate(recs) if r["nch"] == 2 and r["coef"].shape[1] == 960]
+    runs, cur = [], [idx[0]]
+    for a, b in zip(idx, idx[1:]):
+        if b == a + 1:
+            cur.append(b)
+        else:
+            runs.append(cur)
+            cur = [b]
+    runs.append(cur)
+    total = 0
+    for run in runs:
+        if len(run) < 2:
+            continue
+        coef = np.stack([recs[i]["coef"] for i in run])
+        tr = np.array([recs[i]["B"] == 8 for i in run], np.uint8)
+        want = np.stack([recs[i]["out"] for i in run])
+        pcm, _ = synth.synth_batch(np.ascontiguousarray(coef), tr, None)
+        got = pcm.reshape(len(run), 960, 2).transpose(0, 2, 1)
+        # frame 0 of a run has an unknown previous tail (it is the halo); all later frames are checked
+        assert_parity(want[1:], got[1:], fname)
+        total += len(run)
+    nfr, ntr = REAL_FILES[fname]
+    if nfr is not None:
+        assert total == nfr and sum(r["B"] == 8 for r in recs) == ntr
