@@ -182,18 +182,35 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
             for (int k2 = 0; k2 < 15; k2++)
                 __stcs(dst + 30 + k1 + 30 * k2, make_float4(E[0][k2], E[1][k2], O[0][k2], O[1][k2]));
         } else {
+            // generic channel count: channel pair (cb, cb+1) of an interleaved [n][C] frame
             float *dst = p.pcm + f * kFrame * p.C + cb;
             const int C = p.C;
+            if (nch == 2 && (C & 1) == 0) {          // 8-byte aligned {ch, ch+1} pairs
+                __stcs(reinterpret_cast<float2 *>(dst + (58 - 2 * k1) * C), make_float2(H0[0], H0[1]));
+                __stcs(reinterpret_cast<float2 *>(dst + (59 - 2 * k1) * C), make_float2(H1[0], H1[1]));
 #pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch < nch) {
-                    dst[(58 - 2 * k1) * C + ch] = H0[ch];
-                    dst[(59 - 2 * k1) * C + ch] = H1[ch];
+                for (int k2 = 0; k2 < 15; k2++) {
+                    const int n = 60 + 2 * (k1 + 30 * k2);
+                    __stcs(reinterpret_cast<float2 *>(dst + n * C), make_float2(E[0][k2], E[1][k2]));
+                    __stcs(reinterpret_cast<float2 *>(dst + (n + 1) * C), make_float2(O[0][k2], O[1][k2]));
+                }
+            } else if (C == 1) {                     // mono: {y[n], y[n+1]} is contiguous
+                __stcs(reinterpret_cast<float2 *>(dst + 58 - 2 * k1), make_float2(H0[0], H1[0]));
 #pragma unroll
-                    for (int k2 = 0; k2 < 15; k2++) {
-                        const int n = 60 + 2 * (k1 + 30 * k2);
-                        dst[n * C + ch] = E[ch][k2];
-                        dst[(n + 1) * C + ch] = O[ch][k2];
+                for (int k2 = 0; k2 < 15; k2++)
+                    __stcs(reinterpret_cast<float2 *>(dst + 60 + 2 * (k1 + 30 * k2)), make_float2(E[0][k2], O[0][k2]));
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch < nch) {
+                        dst[(58 - 2 * k1) * C + ch] = H0[ch];
+                        dst[(59 - 2 * k1) * C + ch] = H1[ch];
+#pragma unroll
+                        for (int k2 = 0; k2 < 15; k2++) {
+                            const int n = 60 + 2 * (k1 + 30 * k2);
+                            dst[n * C + ch] = E[ch][k2];
+                            dst[(n + 1) * C + ch] = O[ch][k2];
+                        }
                     }
                 }
             }
@@ -279,9 +296,14 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
             for (int j = 0; j < 15; j++) __stcs(dst + lane + 32 * j, s4[lane + 32 * j]);
         } else {
             float *dst = p.pcm + f * kFrame * p.C + cb;
-            for (int idx = lane; idx < 2 * kFrame; idx += 32) {
-                const int n = idx >> 1, ch = idx & 1;
-                if (ch < nch) dst[n * p.C + ch] = stage[idx];
+            if (nch == 2 && (p.C & 1) == 0) {
+                const float2 *s2 = reinterpret_cast<const float2 *>(stage);
+                for (int n = lane; n < kFrame; n += 32) __stcs(reinterpret_cast<float2 *>(dst + n * p.C), s2[n]);
+            } else {
+                for (int idx = lane; idx < 2 * kFrame; idx += 32) {
+                    const int n = idx >> 1, ch = idx & 1;
+                    if (ch < nch) dst[n * p.C + ch] = stage[idx];
+                }
             }
         }
     }

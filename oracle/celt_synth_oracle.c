@@ -421,3 +421,108 @@ NQO_API double nqo_synth_batch(const float *coef, const uint8_t *transient, cons
     free(th);
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ======================================================================
+ * pitch post-filter + de-emphasis + PCM scale
+ * ====================================================================== */
+
+/* celt.c:114-172 comb_filter, in place or not, float build.  The constant
+ * part follows the SSE override the reference actually compiles on x86-64
+ * (celt/x86/pitch_sse.h:104-151: partial sums, four samples per step, loads
+ * before stores -- equivalent to the per-sample order below because T >= 15). */
+static void comb_filter(float *y, const float *x, int T0, int T1, int N, float g0, float g1,
+                        int tapset0, int tapset1)
+{
+    static const float gains[3][3] = {
+        {0.3066406250f, 0.2170410156f, 0.1296386719f},
+        {0.4638671875f, 0.2680664062f, 0.f},
+        {0.7998046875f, 0.1000976562f, 0.f}};
+    float g00, g01, g02, g10, g11, g12, x0, x1, x2, x3, x4;
+    int i;
+    if (g0 == 0 && g1 == 0) {
+        if (x != y) memmove(y, x, N * sizeof(float));
+        return;
+    }
+    g00 = g0 * gains[tapset0][0]; g01 = g0 * gains[tapset0][1]; g02 = g0 * gains[tapset0][2];
+    g10 = g1 * gains[tapset1][0]; g11 = g1 * gains[tapset1][1]; g12 = g1 * gains[tapset1][2];
+    x1 = x[-T1 + 1]; x2 = x[-T1]; x3 = x[-T1 - 1]; x4 = x[-T1 - 2];
+    for (i = 0; i < OVERLAP; i++) {
+        float f;
+        x0 = x[i - T1 + 2];
+        f = g_window[i] * g_window[i];
+        y[i] = x[i]
+             + ((1.0f - f) * g00) * x[i - T0]
+             + ((1.0f - f) * g01) * (x[i - T0 + 1] + x[i - T0 - 1])
+             + ((1.0f - f) * g02) * (x[i - T0 + 2] + x[i - T0 - 2])
+             + (f * g10) * x2
+             + (f * g11) * (x1 + x3)
+             + (f * g12) * (x0 + x4);
+        x4 = x3; x3 = x2; x2 = x1; x1 = x0;
+    }
+    if (g1 == 0) {
+        if (x != y) memmove(y + OVERLAP, x + OVERLAP, (N - OVERLAP) * sizeof(float));
+        return;
+    }
+    for (; i < N; i++)
+        y[i] = (x[i] + g10 * x[i - T1])
+             + (g11 * (x[i - T1 + 1] + x[i - T1 - 1]) + g12 * (x[i - T1 + 2] + x[i - T1 - 2]));
+}
+
+NQO_API void nqo_comb_filter(float *y, float *x, int T0, int T1, int N, float g0, float g1, int tapset0, int tapset1)
+{
+    if (!g_ready) nqo_init_default();
+    comb_filter(y, x, T0, T1, N, g0, g1, tapset0, tapset1);
+}
+
+/* Per-frame side information phase 1 hands to the post stage: the arguments of the two
+ * comb_filter calls at celt_decoder_clean.c:663-669 (old -> cur over [0,120), cur -> new
+ * over [120,N)); layout shared with include/nq_celt_synth.h nq_celt_post_frame. */
+typedef struct {
+    int32_t N;          /* samples per channel of this frame: 120 << LM */
+    int32_t pitch[3];   /* postfilter_period_old, postfilter_period, postfilter_pitch */
+    float gain[3];
+    int32_t tapset[3];
+} post_frame;
+
+enum { HIST = 1026 };   /* COMBFILTER_MAXPERIOD + 2 samples of filtered history, celt.h:187 */
+
+/* comb_filter x2 (celt_decoder_clean.c:658-670) then deemphasis (:723, :192-256) over a run of
+ * frames.  sig [nsamples][C] interleaved celt_sig (the synthesis output), pcm [nsamples][C]
+ * float in [-1,1].  hist_in/out [C][1026]: last filtered samples; mem_in/out [C]: preemph_memD. */
+NQO_API void nqo_post_batch(const float *sig, const post_frame *frames, long nframes, int C,
+                            const float *hist_in, const float *mem_in, float *pcm,
+                            float *hist_out, float *mem_out)
+{
+    const float coef0 = 0.85000610f;   /* mode->preemph[0], static_modes_float.h:583 */
+    long nsamples = 0, f, n0;
+    int c, j;
+    float *buf;
+    if (!g_ready) nqo_init_default();
+    for (f = 0; f < nframes; f++) nsamples += frames[f].N;
+    buf = (float *)calloc((size_t)HIST + nsamples, sizeof(float));
+    for (c = 0; c < C; c++) {
+        float m = mem_in ? mem_in[c] : 0.f;
+        float *x = buf + HIST;
+        if (hist_in) memcpy(buf, hist_in + (size_t)c * HIST, HIST * sizeof(float));
+        else memset(buf, 0, HIST * sizeof(float));
+        for (n0 = 0; n0 < nsamples; n0++) x[n0] = sig[n0 * C + c];
+        n0 = 0;
+        for (f = 0; f < nframes; f++) {
+            const post_frame *p = &frames[f];
+            float *o = x + n0;
+            comb_filter(o, o, p->pitch[0], p->pitch[1], 120, p->gain[0], p->gain[1], p->tapset[0], p->tapset[1]);
+            if (p->N > 120)
+                comb_filter(o + 120, o + 120, p->pitch[1], p->pitch[2], p->N - 120, p->gain[1], p->gain[2],
+                            p->tapset[1], p->tapset[2]);
+            for (j = 0; j < p->N; j++) {
+                float tmp = o[j] + m + 1e-30f;
+                m = coef0 * tmp;
+                pcm[(n0 + j) * C + c] = tmp * (1 / 32768.f);
+            }
+            n0 += p->N;
+        }
+        if (hist_out) memcpy(hist_out + (size_t)c * HIST, x + nsamples - HIST, HIST * sizeof(float));
+        if (mem_out) mem_out[c] = m;
+    }
+    free(buf);
+}

@@ -50,6 +50,8 @@ def lib():
         L.nqo_compute_inv_mdcts.argtypes = [C.c_int, fp, C.POINTER(fp), C.c_int, C.c_int]
         L.nqo_synth_batch.argtypes = [fp, C.c_void_p, fp, fp, fp, C.c_long, C.c_int, C.c_int]
         L.nqo_synth_batch.restype = C.c_double
+        L.nqo_comb_filter.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.nqo_post_batch.argtypes = [fp, C.c_void_p, C.c_long, C.c_int, fp, fp, fp, fp, fp]
         # Install the reference's exact static tables when the fixture exists
         # (one-ulp differences from the formula otherwise; see the C header).
         if os.path.exists(GOLDEN_TABLES):
@@ -123,3 +125,51 @@ def compute_inv_mdcts(shortBlocks: int, X: np.ndarray, out_mem, Cn: int, LM: int
     fp = C.POINTER(C.c_float)
     outs = (fp * Cn)(*[_fp(o) for o in out_mem])
     lib().nqo_compute_inv_mdcts(int(shortBlocks), _fp(X), outs, int(Cn), int(LM))
+
+
+# ---- post-filter + de-emphasis ------------------------
+POST_FRAME_DTYPE = np.dtype([("N", np.int32), ("pitch", np.int32, 3), ("gain", np.float32, 3),
+                             ("tapset", np.int32, 3)])
+HIST = 1026
+
+
+def comb_filter(buf: np.ndarray, start: int, T0, T1, N, g0, g1, tapset0, tapset1) -> None:
+    """celt.c:114 in place on buf[start:start+N]; buf[:start] is the history."""
+    assert buf.dtype == np.float32 and buf.flags.c_contiguous and start >= max(T0, T1) + 2
+    p = C.cast(buf.ctypes.data + 4 * start, C.POINTER(C.c_float))
+    lib().nqo_comb_filter(p, p, int(T0), int(T1), int(N), float(g0), float(g1), int(tapset0), int(tapset1))
+
+
+def post_batch(sig, frames, hist_in=None, mem_in=None):
+    """comb_filter x2 + deemphasis over a run of frames (celt_decoder_clean.c:658-670, :723).
+    sig [nsamples][C] celt_sig, frames: POST_FRAME_DTYPE [nframes].
+    Returns (pcm [nsamples][C], hist_out [C][1026], mem_out [C])."""
+    sig = np.ascontiguousarray(sig, np.float32)
+    frames = np.ascontiguousarray(frames, POST_FRAME_DTYPE)
+    nsamples, Cn = sig.shape
+    assert int(frames["N"].sum()) == nsamples
+    hi = None if hist_in is None else np.ascontiguousarray(hist_in, np.float32)
+    mi = None if mem_in is None else np.ascontiguousarray(mem_in, np.float32)
+    pcm = np.zeros_like(sig)
+    ho = np.zeros((Cn, HIST), np.float32)
+    mo = np.zeros(Cn, np.float32)
+    lib().nqo_post_batch(_fp(sig), frames.ctypes.data_as(C.c_void_p), len(frames), Cn, _fp(hi), _fp(mi),
+                         _fp(pcm), _fp(ho), _fp(mo))
+    return pcm, ho, mo
+
+
+def post_frames_from_records(recs):
+    """Side info for the post stage from oracle.ref.decode_file(..., record=True) records."""
+    out = np.zeros(len(recs), POST_FRAME_DTYPE)
+    for i, r in enumerate(recs):
+        c = r["comb"]
+        nn = r["coef"].shape[1]
+        out[i]["N"] = nn
+        # call 1: (old -> cur); call 2 (LM > 0): (cur -> new)
+        out[i]["pitch"][0], out[i]["pitch"][1] = int(c[0][1]), int(c[0][2])
+        out[i]["gain"][0], out[i]["gain"][1] = c[0][3], c[0][4]
+        out[i]["tapset"][0], out[i]["tapset"][1] = int(c[0][5]), int(c[0][6])
+        if nn > 120:
+            assert int(c[1][1]) == int(c[0][2]) and c[1][3] == c[0][4]
+            out[i]["pitch"][2], out[i]["gain"][2], out[i]["tapset"][2] = int(c[1][2]), c[1][4], int(c[1][6])
+    return out

@@ -44,6 +44,10 @@ def lib():
         L.nqref_record_count.restype = C.c_long
         L.nqref_record_floats.restype = C.c_size_t
         L.nqref_record_copy.argtypes = [fp]
+        L.nqref_comb_floats.restype = C.c_size_t
+        L.nqref_comb_copy.argtypes = [fp]
+        L.nqref_comb_filter.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.nqref_deemphasis.argtypes = [C.POINTER(fp), fp, C.c_int, C.c_int, fp]
         _lib = L
     return _lib
 
@@ -124,13 +128,47 @@ def decode_file(path: str, record: bool = False):
     if record:
         flat = np.zeros(L.nqref_record_floats(), np.float32)
         L.nqref_record_copy(_fp(flat))
+        comb = np.zeros(L.nqref_comb_floats(), np.float32)
+        L.nqref_comb_copy(_fp(comb))
+        comb = comb.reshape(-1, 8)
         L.nqref_record_free()
         recs = []
+        cpos = 0
         p = 0
         while p < flat.size:
             nch, shift, B, nn = flat[p:p + 4].view(np.int32)
             p += 4
             coef = flat[p:p + nch * nn].reshape(nch, nn); p += nch * nn
             out = flat[p:p + nch * nn].reshape(nch, nn); p += nch * nn
-            recs.append(dict(nch=int(nch), shift=int(shift), B=int(B), coef=coef, out=out))
+            # comb_filter calls of this synthesis record: per channel 1 call (LM = 0) or 2 (LM > 0)
+            # (celt_decoder_clean.c:663-669); LM follows from the record's frame length.
+            ncalls = nch * (1 if nn == 120 else 2)
+            calls = comb[cpos:cpos + ncalls]; cpos += ncalls
+            recs.append(dict(nch=int(nch), shift=int(shift), B=int(B), coef=coef, out=out, comb=calls))
+        assert cpos == len(comb), (cpos, len(comb))
     return pcm, recs
+
+
+def header_info():
+    """(pre_skip, output_gain) of the file decoded last (opusfile OpusHead)."""
+    L = lib()
+    return int(L.nqref_last_pre_skip()), int(L.nqref_last_output_gain())
+
+
+def comb_filter(buf: np.ndarray, start: int, T0, T1, N, g0, g1, tapset0, tapset1) -> None:
+    """celt.c:114 in place on buf[start:start+N] (buf[:start] is the history, >= max(T)+2 long)."""
+    assert buf.dtype == np.float32 and buf.flags.c_contiguous and start >= max(T0, T1) + 2
+    p = C.cast(buf.ctypes.data + 4 * start, C.POINTER(C.c_float))
+    lib().nqref_comb_filter(p, p, int(T0), int(T1), int(N), float(g0), float(g1), int(tapset0), int(tapset1))
+
+
+def deemphasis(x: np.ndarray, mem: np.ndarray) -> np.ndarray:
+    """celt_decoder_clean.c:192: x [C][N] celt_sig -> pcm [N][C]; mem [C] updated in place."""
+    Cn, N = x.shape
+    x = np.ascontiguousarray(x, np.float32)
+    fp = C.POINTER(C.c_float)
+    rows = (fp * Cn)(*[C.cast(x.ctypes.data + 4 * N * c, fp) for c in range(Cn)])
+    pcm = np.zeros((N, Cn), np.float32)
+    assert mem.dtype == np.float32 and mem.shape == (Cn,)
+    lib().nqref_deemphasis(rows, _fp(pcm), N, Cn, _fp(mem))
+    return pcm

@@ -185,6 +185,7 @@ NQREF_API double nqref_synth_batch_mt(const float *coef, const uint8_t *transien
 typedef struct {
     int active;
     float *buf; size_t len, cap;   /* in floats */
+    float *cbuf; size_t clen, ccap; /* comb_filter call log, 8 floats per call */
     long nrecords;
     int b;                         /* sub-block counter inside a stride-B group */
     float *xbase[2], *obase[2];
@@ -233,6 +234,44 @@ void nqref_tap_mdct(const mdct_lookup *l, float *in, float *out,
     if (g_rec.active) rec_group(1, shift, stride, &in, &out);
 }
 
+/* comb_filter tap: one 8-float record per call {N, T0, T1, g0, g1, tapset0, tapset1, 0}. */
+void nqref_tap_comb_filter(float *y, float *x, int T0, int T1, int N, float g0, float g1,
+                           int tapset0, int tapset1, const float *window, int overlap)
+{
+    comb_filter(y, x, T0, T1, N, g0, g1, tapset0, tapset1, window, overlap);
+    if (g_rec.active) {
+        float *r;
+        if (g_rec.clen + 8 > g_rec.ccap) {
+            g_rec.ccap = g_rec.ccap ? g_rec.ccap * 2 : (1u << 16);
+            g_rec.cbuf = (float *)realloc(g_rec.cbuf, g_rec.ccap * sizeof(float));
+        }
+        r = g_rec.cbuf + g_rec.clen;
+        r[0] = (float)N; r[1] = (float)T0; r[2] = (float)T1; r[3] = g0; r[4] = g1;
+        r[5] = (float)tapset0; r[6] = (float)tapset1; r[7] = 0;
+        g_rec.clen += 8;
+    }
+}
+
+static int g_last_pre_skip, g_last_output_gain;
+NQREF_API int nqref_last_pre_skip(void) { return g_last_pre_skip; }
+NQREF_API int nqref_last_output_gain(void) { return g_last_output_gain; }
+NQREF_API size_t nqref_comb_floats(void) { return g_rec.clen; }
+NQREF_API void nqref_comb_copy(float *dst) { memcpy(dst, g_rec.cbuf, g_rec.clen * sizeof(float)); }
+
+/* comb_filter (celt.c:114) and deemphasis (celt_decoder_clean.c:192) on caller buffers, for
+ * pinning the oracle's restatement.  x points INSIDE a buffer with >= T+2 samples of history. */
+NQREF_API void nqref_comb_filter(float *y, float *x, int T0, int T1, int N, float g0, float g1,
+                                 int tapset0, int tapset1)
+{
+    comb_filter(y, x, T0, T1, N, g0, g1, tapset0, tapset1, the_mode()->window, OVL);
+}
+
+NQREF_API void nqref_deemphasis(float **in, float *pcm, int N, int C, float *mem)
+{
+    float scratch[FRAME];
+    deemphasis(in, pcm, N, C, 1, the_mode()->preemph, mem, scratch);
+}
+
 /* Decode an in-memory Ogg Opus file the way src/OpusDecoder.cpp:57-119 does
  * (op_test_memory/op_test_open/op_read_float loop).  Returns samples per
  * channel decoded (<0 on error).  pcm may be NULL (count only).  If record
@@ -248,8 +287,10 @@ NQREF_API long nqref_decode_memory(const unsigned char *data, size_t nbytes,
     if (!of) return -1;
     if (op_test_open(of) != 0) return -2;   /* frees of on failure */
     ch = op_head(of, 0)->channel_count;
+    g_last_pre_skip = (int)op_head(of, 0)->pre_skip;
+    g_last_output_gain = op_head(of, 0)->output_gain;
     if (channels_out) *channels_out = ch;
-    g_rec.active = record; g_rec.len = 0; g_rec.nrecords = 0; g_rec.b = 0;
+    g_rec.active = record; g_rec.len = 0; g_rec.clen = 0; g_rec.nrecords = 0; g_rec.b = 0;
     for (;;) {
         float *dst = scratch;
         int room = (int)(sizeof scratch / sizeof scratch[0]);
@@ -276,4 +317,5 @@ NQREF_API void nqref_record_copy(float *dst) { memcpy(dst, g_rec.buf, g_rec.len 
 NQREF_API void nqref_record_free(void)
 {
     free(g_rec.buf); g_rec.buf = NULL; g_rec.len = g_rec.cap = 0; g_rec.nrecords = 0;
+    free(g_rec.cbuf); g_rec.cbuf = NULL; g_rec.clen = g_rec.ccap = 0;
 }

@@ -16,6 +16,13 @@ Outputs (all small):
                      call sites while the reference decodes the bundled
                      sb-reverie.opus / sb-reverie-60ms-frames.opus / short.opus
                      (coefficients in, out_syn out), incl. transient frames
+  post_cases.npz     SURVEY.md 8(f) row 1: single comb_filter / deemphasis calls of
+                     the compiled reference on seeded inputs, and the LAST 26 frames
+                     of short.opus (active post-filter, tapset changes, a transient
+                     and the final 2.5 ms LM=0 frame): out_syn in, side info, and the
+                     reference decoder's final PCM out.  The incoming filter state of
+                     that run comes from the oracle, after the generator has checked
+                     that the oracle reproduces the WHOLE file's PCM bit-exactly.
 """
 import os
 import shutil
@@ -102,6 +109,43 @@ def main():
         real[f"{tag}.transient"] = np.array([recs[i]["B"] == 8 for i in idx], np.uint8)
         real[f"{tag}.out"] = np.stack([recs[i]["out"] for i in idx])            # [13][2][960]
     np.savez_compressed(f"{HERE}/real_frames.npz", **real)
+
+    from oracle import port
+    post = {}
+    for i, (T0, T1, g0, g1, ts0, ts1, N) in enumerate([(15, 15, 0.75, 0.75, 0, 0, 840), (1022, 15, 0.5625, 0.09375, 2, 1, 840),
+                                                      (163, 650, 0.28125, 0.0, 0, 2, 840), (300, 77, 0.0, 0.375, 1, 0, 120),
+                                                      (40, 41, 0.0, 0.0, 0, 0, 120), (100, 100, 0.46875, 0.46875, 1, 1, 120)]):
+        buf = rng.uniform(-3000, 3000, 1026 + N).astype(np.float32)
+        post[f"comb{i}.args"] = np.array([T0, T1, N, g0, g1, ts0, ts1], np.float64)
+        post[f"comb{i}.before"] = buf.copy()
+        ref.comb_filter(buf, 1026, T0, T1, N, g0, g1, ts0, ts1)
+        post[f"comb{i}.after"] = buf
+    x = rng.uniform(-6000, 6000, (2, 960)).astype(np.float32)
+    mem = np.array([123.5, -77.25], np.float32)
+    post["deemph.x"], post["deemph.mem_in"] = x, mem.copy()
+    post["deemph.pcm"] = ref.deemphasis(x, mem)
+    post["deemph.mem_out"] = mem
+    for fname in ("short.opus", "sb-reverie.opus", "sb-reverie-60ms-frames.opus"):
+        pcm, recs = ref.decode_file(f"{REF}/test_data/{fname}", record=True)
+        pre_skip, gain = ref.header_info()
+        assert gain == 0
+        sig = np.concatenate([r["out"].T for r in recs], axis=0)
+        frames = port.post_frames_from_records(recs)
+        full, _, _ = port.post_batch(sig, frames)
+        # opusfile drops pre_skip samples at the head and trims the tail (opusfile.c:2673-2721)
+        assert np.array_equal(full[pre_skip:pre_skip + len(pcm)].view(np.uint32), pcm.view(np.uint32)), fname
+        if fname == "short.opus":
+            k = len(recs) - 26
+            n0 = int(frames["N"][:k].sum())
+            _, hist, mem = port.post_batch(sig[:n0], frames[:k])
+            post["short_tail.sig"] = sig[n0:]
+            post["short_tail.frames"] = frames[k:]
+            post["short_tail.hist_in"], post["short_tail.mem_in"] = hist, mem
+            post["short_tail.pcm"] = full[n0:]                      # == reference PCM where the file has it
+            post["short_tail.n_in_file"] = np.int64(pre_skip + len(pcm) - n0)
+            post["short_tail.transient"] = np.array([r["B"] == 8 for r in recs[k:]], np.uint8)
+            post["short_tail.coef_first"] = recs[k]["coef"]
+    np.savez_compressed(f"{HERE}/post_cases.npz", **post)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

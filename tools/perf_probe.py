@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Device-resident throughput of the batched synthesis for several shapes
+(channels x transient fraction).  Diagnostic only; bench.py is the contract."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import libnyquist_b200 as nq
+
+def run(synth, frames, C, p_tr, steps=5):
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    coef = torch.empty((frames, C, 960), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g)
+    tr = (torch.rand(frames, generator=g, device=dev) < p_tr).to(torch.uint8)
+    pcm = torch.empty((frames * 960, C), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        synth.synth_batch_torch(coef, tr, out=pcm, want_tail=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        synth.synth_batch_torch(coef, tr, out=pcm, want_tail=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    gbs = frames * C * 960 * 8 / (ms * 1e-3) / 1e9
+    return dict(frames=frames, C=C, p_transient=p_tr, ms=round(ms, 3), GBps=round(gbs, 1),
+                Mframes_per_s=round(frames / ms / 1e3, 2), frac_of_6527=round(gbs / 6527.5, 3))
+
+if __name__ == "__main__":
+    with nq.CeltSynth(0) as s:
+        for frames, C, p in [(2_000_000, 2, 0.0), (2_000_000, 2, 0.028), (2_000_000, 2, 0.2), (2_000_000, 2, 1.0),
+                             (4_000_000, 1, 0.028), (500_000, 8, 0.028), (1_300_000, 3, 0.028),
+                             (20_000, 2, 0.028), (2_000, 2, 0.028)]:
+            print(json.dumps(run(s, frames, C, p)), flush=True)
