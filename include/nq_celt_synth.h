@@ -102,6 +102,35 @@ NQ_API int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const u
                                     const float *tail_in, float *pcm_out, float *tail_out,
                                     int64_t nframes, int C);
 
+/* Opus multistream batch: `streams` independent CELT decoders, the first
+ * `coupled_streams` of them stereo, routed to `channels` output channels by
+ * `mapping` -- the arguments of opus_multistream_decoder_create
+ * (third_party/opus/libopus/src/opus_multistream_decoder.c:110).  Replaces, for
+ * nframes frames, the per-stream compute_inv_mdcts calls AND the strided
+ * channel copy opus_multistream_decode_native does afterwards (:237-299,
+ * get_left/right/mono_channel opus_multistream.c:57-91): the interleave is
+ * fused into the synthesis kernel's store pass.
+ *
+ *   D = streams + coupled_streams decoded channels; decoded channel d is
+ *       stream d/2 (left, right) for d < 2*coupled_streams, else the mono
+ *       stream d - coupled_streams
+ *   coef       [nframes][D][960]   rows in decoded-channel order
+ *   transient  [nframes][streams]  every stream has its own block switching
+ *   tail_in / tail_out [D][60], halo_coef [D][960] (device), halo_transient
+ *              [streams] (HOST pointer; needed with halo_coef)
+ *   mapping    [channels] (HOST pointer): output channel c carries decoded
+ *              channel mapping[c]; 255 = silent channel; a decoded channel may
+ *              feed several outputs or none
+ *   pcm_out    [nframes*960][channels]
+ * At most 14 streams per batch (NQ_UNIMPLEMENTED beyond: one warp per stream,
+ * 14 warps per SM).  All pointers except mapping / halo_transient are device
+ * pointers; enqueued on `stream`, no synchronisation. */
+NQ_API int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient,
+                                         const float *tail_in, const float *halo_coef,
+                                         const uint8_t *halo_transient, float *pcm_out, float *tail_out,
+                                         int64_t nframes, int channels, int streams, int coupled_streams,
+                                         const unsigned char *mapping, void *stream);
+
 /* Same as _host, frames sharded contiguously over `ndev` devices (devices[i]
  * = CUDA ordinal; NULL => 0..ndev-1) with one host thread + context per
  * device and NO device-to-device traffic: a shard that starts mid-stream

@@ -33,7 +33,8 @@ NQ_OK = 0
 EXPORTED_SYMBOLS = [
     "nq_celt_ctx_create", "nq_celt_ctx_destroy", "nq_celt_strerror", "nq_celt_last_error",
     "nq_celt_device_count", "nq_celt_launch_count", "nq_celt_host_alloc", "nq_celt_host_free",
-    "nq_celt_synth_batch_device", "nq_celt_synth_batch_host", "nq_celt_synth_batch_host_multi",
+    "nq_celt_synth_batch_device", "nq_celt_synth_batch_device_ms", "nq_celt_synth_batch_host",
+    "nq_celt_synth_batch_host_multi",
     "nq_clt_mdct_backward", "nq_clt_mdct_backward_B1_C2", "nq_celt_mdct_backward_host",
     "nq_compute_inv_mdcts", "nq_opus_ifft_host", "processMDCTCuda", "processMDCTCudaB1C2", "cleanupCudaBuffers",
     "printCudaVersion", "nq_celt_debug_tables",
@@ -73,6 +74,8 @@ def load_library():
     L.nq_celt_host_free.argtypes = [vp]
     L.nq_celt_synth_batch_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int64, C.c_int, vp]
     L.nq_celt_synth_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int]
+    L.nq_celt_synth_batch_device_ms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                                vp, vp]
     L.nq_celt_synth_batch_host_multi.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int]
     L.nq_clt_mdct_backward.argtypes = [vp, fp, fp, fp, C.c_int, C.c_int, C.c_int]
     L.nq_clt_mdct_backward.restype = None
@@ -248,6 +251,35 @@ class CeltSynth:
                                     0 if tail_in is None else tail_in.data_ptr(),
                                     0 if halo_coef is None else halo_coef.data_ptr(), halo_transient,
                                     pcm.data_ptr(), 0 if tail is None else tail.data_ptr(), nframes, Cn, st)
+        return pcm, tail
+
+
+    def synth_batch_ms_torch(self, coef, transient, streams: int, coupled_streams: int, mapping,
+                             tail_in=None, halo_coef=None, halo_transient=None, out=None, want_tail=True,
+                             stream=None):
+        """Opus multistream batch (opus_multistream_decoder.c:110, :237-299): coef cuda f32
+        [nframes][streams+coupled][960], transient cuda u8 [nframes][streams], mapping: sequence of
+        `channels` decoded-channel indices (255 = silent).  Returns (pcm [nframes*960][channels], tail)."""
+        import torch
+        D = streams + coupled_streams
+        assert coef.is_cuda and coef.dtype == torch.float32 and coef.is_contiguous()
+        assert transient.is_cuda and transient.dtype == torch.uint8 and transient.is_contiguous()
+        nframes = coef.shape[0]
+        assert coef.shape == (nframes, D, FRAME) and transient.shape == (nframes, streams)
+        mp = np.ascontiguousarray(mapping, np.uint8)
+        ch = mp.size
+        pcm = out if out is not None else torch.empty((nframes * FRAME, ch), dtype=torch.float32, device=coef.device)
+        tail = torch.empty((D, HALF_OVERLAP), dtype=torch.float32, device=coef.device) if want_tail else None
+        st = (stream if stream is not None else torch.cuda.current_stream(coef.device)).cuda_stream
+        if st == 0:
+            st = 1
+        ht = None if halo_transient is None else np.ascontiguousarray(halo_transient, np.uint8)
+        self._check(self._L.nq_celt_synth_batch_device_ms(
+            self._h, C.c_void_p(coef.data_ptr()), C.c_void_p(transient.data_ptr()),
+            C.c_void_p(0 if tail_in is None else tail_in.data_ptr()),
+            C.c_void_p(0 if halo_coef is None else halo_coef.data_ptr()), _vp(ht), C.c_void_p(pcm.data_ptr()),
+            C.c_void_p(0 if tail is None else tail.data_ptr()), nframes, ch, int(streams), int(coupled_streams),
+            _vp(mp), C.c_void_p(st)))
         return pcm, tail
 
 

@@ -126,11 +126,10 @@ int fail(nq_celt_ctx *ctx, int code, const char *fmt, ...)
 // Splits nframes into runs of consecutive frames, one run per warp-item.
 // Every run after the first re-computes one extra frame (its predecessor) to
 // obtain the raw tail, so runs are kept long: >= 8 frames when the batch
-// allows, and otherwise just long enough to give every resident warp one run.
-void plan_runs(long long nframes, int npairs, int num_sms, long long *frames_per_run, long long *nruns)
+// allows, and otherwise just long enough to give every resident item one run.
+void plan_runs(long long nframes, long long resident_items, long long *frames_per_run, long long *nruns)
 {
-    const long long total_warps = (long long)num_sms * kWarpsPerCta;
-    long long target_runs = total_warps / npairs;
+    long long target_runs = resident_items;
     if (target_runs < 1) target_runs = 1;
     long long K = (nframes + target_runs - 1) / target_runs;
     if (K < 8) K = 8;
@@ -139,9 +138,34 @@ void plan_runs(long long nframes, int npairs, int num_sms, long long *frames_per
     *nruns = (nframes + K - 1) / K;
 }
 
-int enqueue_synth(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const float *tail_in,
-                  const float *halo_coef, int halo_transient, float *pcm, float *tail_out, long long nframes,
-                  int C, cudaStream_t stream)
+// Channel layout of a batch: the arguments of opus_multistream_decoder_create
+// (opus_multistream_decoder.c:110).  Decoded channel d is row d of a frame's coefficients:
+// coupled stream s -> rows 2s, 2s+1; mono stream s -> row s + coupled (opus_multistream.c:57-91).
+struct Layout {
+    int C = 0;          // output channels
+    int streams = 0;
+    int coupled = 0;
+    int D = 0;          // streams + coupled
+    bool per_stream_flags = false;
+    bool identity = true;
+    unsigned char mapping[kMaxChannels + 1] = {};
+};
+
+// Plain C-channel batch (compute_inv_mdcts with C channels sharing one transient flag):
+// pairs (0,1), (2,3), ... plus a trailing mono channel; identity mapping.
+Layout plain_layout(int C)
+{
+    Layout L;
+    L.C = L.D = C;
+    L.coupled = C / 2;
+    L.streams = (C + 1) / 2;
+    for (int c = 0; c < C; c++) L.mapping[c] = (unsigned char)c;
+    return L;
+}
+
+int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8_t *transient, const float *tail_in,
+                  const float *halo_coef, unsigned halo_transient_bits, float *pcm, float *tail_out, long long nframes,
+                  cudaStream_t stream)
 {
     SynthParams p;
     memset(&p, 0, sizeof p);
@@ -149,18 +173,58 @@ int enqueue_synth(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient,
     p.transient = transient;
     p.tail_in = tail_in;
     p.halo_coef = tail_in ? nullptr : halo_coef;
-    p.halo_transient = halo_transient ? 1 : 0;
+    p.halo_transient = (int)halo_transient_bits;
     p.pcm = pcm;
     p.tail_out = tail_out;
     p.tables = ctx->d_fast;
     p.nframes = nframes;
-    p.C = C;
-    p.npairs = (C + 1) / 2;
-    p.flag_stride = 1;
-    p.flag_per_pair = 0;
-    plan_runs(nframes, p.npairs, ctx->num_sms, &p.frames_per_run, &p.nruns);
-    NQ_CUDA(ctx, launch_synth(p, ctx->num_sms, stream, nullptr));
+    p.D = L.D;
+    p.C = L.C;
+    p.npairs = (L.D + 1) / 2;
+    p.nstreams = L.streams;
+    p.flag_stride = L.per_stream_flags ? L.streams : 1;
+    p.flag_per_stream = L.per_stream_flags ? 1 : 0;
+    const int mode = synth_mode(L.D, L.C, L.streams, L.identity);
+    if (mode == kModeDirect && (!L.identity || L.per_stream_flags))
+        return fail(ctx, NQ_UNIMPLEMENTED, "a channel mapping needs streams <= %d (got %d)", kMaxGroupStreams, L.streams);
+    long long resident = (long long)ctx->num_sms * kWarpsPerCta / p.npairs;
+    if (mode == kModeGroup) {
+        resident = (long long)ctx->num_sms * groups_per_cta(L.streams);
+        p.store_threads = group_store_threads(L.C, L.streams);
+        for (int s = 0; s < L.streams; s++) {
+            p.streams[s].nch = s < L.coupled ? 2 : 1;
+            p.streams[s].row = (uint8_t)(s < L.coupled ? 2 * s : s + L.coupled);
+            p.streams[s].flag_col = (uint8_t)(L.per_stream_flags ? s : 0);
+        }
+        for (int c = 0; c < L.C; c++) {
+            const int d = L.mapping[c];
+            if (d == 255) p.chan_src[c] = 0xffffu;   // muted channel, opus_multistream_decoder.c:291-299
+            else if (d < 2 * L.coupled) p.chan_src[c] = (uint16_t)(((d >> 1) << 1) | (d & 1));
+            else p.chan_src[c] = (uint16_t)((d - L.coupled) << 1);
+        }
+    }
+    plan_runs(nframes, resident, &p.frames_per_run, &p.nruns);
+    NQ_CUDA(ctx, launch_synth(p, mode, ctx->num_sms, stream, nullptr));
     ctx->launches++;
+    return NQ_OK;
+}
+
+int check_layout(nq_celt_ctx *ctx, int channels, int streams, int coupled, const unsigned char *mapping, Layout *L)
+{
+    // opus_multistream_decoder_init, opus_multistream_decoder.c:63-108 (validate_layout, opus_multistream.c:40-55)
+    if (channels < 1 || channels > 255 || streams < 1 || coupled < 0 || coupled > streams || streams + coupled > 255 || !mapping)
+        return fail(ctx, NQ_BAD_ARG, "channels=%d streams=%d coupled_streams=%d", channels, streams, coupled);
+    L->C = channels;
+    L->streams = streams;
+    L->coupled = coupled;
+    L->D = streams + coupled;
+    L->per_stream_flags = true;
+    L->identity = false;
+    for (int c = 0; c < channels; c++) {
+        if (mapping[c] != 255 && mapping[c] >= L->D)
+            return fail(ctx, NQ_BAD_ARG, "mapping[%d]=%d names no decoded channel (streams+coupled=%d)", c, mapping[c], L->D);
+        L->mapping[c] = mapping[c];
+    }
     return NQ_OK;
 }
 
@@ -319,8 +383,41 @@ int nq_celt_synth_batch_device(nq_celt_ctx *ctx, const float *coef, const uint8_
         (halo_coef && (reinterpret_cast<uintptr_t>(halo_coef) & 15)))
         return fail(ctx, NQ_BAD_ARG, "coef, halo_coef and pcm_out must be 16-byte aligned device pointers");
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    return enqueue_synth(ctx, coef, transient, tail_in, halo_coef, halo_transient, pcm_out, tail_out, nframes, C,
-                         stream ? (cudaStream_t)stream : ctx->stream);
+    return enqueue_synth(ctx, plain_layout(C), coef, transient, tail_in, halo_coef, halo_transient ? 1u : 0u, pcm_out,
+                         tail_out, nframes, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const float *tail_in,
+                                  const float *halo_coef, const uint8_t *halo_transient, float *pcm_out,
+                                  float *tail_out, int64_t nframes, int channels, int streams, int coupled_streams,
+                                  const unsigned char *mapping, void *stream)
+{
+    if (!ctx) return NQ_BAD_ARG;
+    Layout L;
+    int rc = check_layout(ctx, channels, streams, coupled_streams, mapping, &L);
+    if (rc != NQ_OK) return rc;
+    if (nframes < 0) return fail(ctx, NQ_BAD_ARG, "nframes=%lld", (long long)nframes);
+    if (L.streams > kMaxGroupStreams)
+        return fail(ctx, NQ_UNIMPLEMENTED, "at most %d streams per multistream batch (got %d)", kMaxGroupStreams, streams);
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if (nframes == 0) {
+        if (tail_out) {
+            if (tail_in) NQ_CUDA(ctx, cudaMemcpyAsync(tail_out, tail_in, sizeof(float) * L.D * kHalfOvl, cudaMemcpyDeviceToDevice, st));
+            else NQ_CUDA(ctx, cudaMemsetAsync(tail_out, 0, sizeof(float) * L.D * kHalfOvl, st));
+        }
+        return NQ_OK;
+    }
+    if (!coef || !transient || !pcm_out) return fail(ctx, NQ_BAD_ARG, "null coef/transient/pcm_out");
+    if ((reinterpret_cast<uintptr_t>(coef) & 15) || (reinterpret_cast<uintptr_t>(pcm_out) & 15) ||
+        (halo_coef && (reinterpret_cast<uintptr_t>(halo_coef) & 15)))
+        return fail(ctx, NQ_BAD_ARG, "coef, halo_coef and pcm_out must be 16-byte aligned device pointers");
+    unsigned halo_bits = 0;
+    if (halo_coef && !tail_in) {
+        if (!halo_transient) return fail(ctx, NQ_BAD_ARG, "halo_coef needs halo_transient[streams] (host pointer)");
+        for (int s = 0; s < streams; s++) halo_bits |= (halo_transient[s] ? 1u : 0u) << s;
+    }
+    return enqueue_synth(ctx, L, coef, transient, tail_in, halo_coef, halo_bits, pcm_out, tail_out, nframes, st);
 }
 
 }  // extern "C"
@@ -381,9 +478,10 @@ int synth_host_range(nq_celt_ctx *ctx, const float *coef, const uint8_t *transie
         NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags[s], transient + f0, (size_t)n, cudaMemcpyHostToDevice, st));
         if (i > 0) NQ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->kernel_done[(i - 1) % S], 0));
         const bool first_with_halo = (i == 0 && use_halo);
-        int rc = enqueue_synth(ctx, ctx->d_in[s], ctx->d_flags[s], first_with_halo ? nullptr : ctx->d_tail[(i + 1) & 1],
-                               first_with_halo ? ctx->d_halo : nullptr, halo_transient, ctx->d_out[s],
-                               ctx->d_tail[i & 1], n, C, st);
+        int rc = enqueue_synth(ctx, plain_layout(C), ctx->d_in[s], ctx->d_flags[s],
+                               first_with_halo ? nullptr : ctx->d_tail[(i + 1) & 1],
+                               first_with_halo ? ctx->d_halo : nullptr, halo_transient ? 1u : 0u, ctx->d_out[s],
+                               ctx->d_tail[i & 1], n, st);
         if (rc != NQ_OK) return rc;
         NQ_CUDA(ctx, cudaEventRecord(ctx->kernel_done[s], st));
         NQ_CUDA(ctx, cudaMemcpyAsync(pcm_out + f0 * row, ctx->d_out[s], n * row * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -32,6 +32,12 @@
 //     60 = 30 x 2, the radix-2 step and the sub-block to sub-block tail are
 //     warp shuffles; output is staged through the transpose buffer so global
 //     stores stay 128-bit and coalesced.
+//   * channel layouts other than plain stereo (mono, 3, 8 channels, Opus
+//     multistream with a channel mapping): a GROUP of warps, one per stream,
+//     walks the run in lock-step; each warp leaves its frame as a [960][2]
+//     plane in its (idle) transpose buffer, and after one named barrier the
+//     group writes the interleaved [960][C] frame with contiguous float4
+//     stores -- the multistream channel mapping is a gather in this pass.
 // No tensor cores: this is an FFT, not a dense contraction.
 #include "celt_synth_kernels.cuh"
 #include "celt_fft_codelets.cuh"
@@ -84,15 +90,71 @@ struct __align__(16) WarpSmem {
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp smem slice must keep 16-byte alignment");
 static_assert((kInRowFloats * 4) % 16 == 0, "TMA destination rows must be 16-byte aligned");
 
+constexpr int kWarpSmemFloats = int(sizeof(WarpSmem) / 4);
+constexpr int kPlaneOffFloats = 2 * kInRowFloats;   // offsetof(WarpSmem, x) / 4
+
 size_t fast_kernel_smem_bytes() { return sizeof(FastTables) + kWarpsPerCta * sizeof(WarpSmem); }
+
+// Group mode: the warps of one group (one per stream) and their cooperative store pass.
+// The output frame [960][C] is written as 240*C float4; thread tg of the first T2 threads
+// of the group owns float4 q = tg + T2*i.  T2 is chosen on the host so that 4*T2 is a multiple
+// of C: the four output channels a thread serves are then the same in every iteration, and
+// only the sample index advances (by 4*T2/C).
+struct GroupCtx {
+    uint32_t src[4];       // shared-memory byte address of this thread's four elements at iteration 0
+    uint32_t step;         // byte advance per iteration: (4*T2/C) samples * 8 bytes (planes are [960][2])
+    int q0, T2, niter;     // first float4, stride, iterations (0 for the threads beyond T2)
+    int T, bar_id;         // threads in the group, its named barrier (1..15)
+    unsigned mute;         // bit j: element j belongs to a silent output channel
+    bool pending;          // the previous frame's store pass may still be reading the planes
+};
+
+__device__ __forceinline__ void group_sync(const GroupCtx &g)
+{
+    if (g.T == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "r"(g.T) : "memory");
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// Interleaved output frame [960][C] from the group's planes: output channel c is decoded
+// channel mapping[c] (a gather, opus_multistream_decoder.c:260-299) or silence.
+__device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *frame_out)
+{
+    float4 *dst = reinterpret_cast<float4 *>(frame_out) + g.q0;
+    uint32_t a0 = g.src[0], a1 = g.src[1], a2 = g.src[2], a3 = g.src[3];
+#pragma unroll 5
+    for (int i = 0; i < g.niter; i++) {
+        float4 v;
+        v.x = lds_f32(a0);
+        v.y = lds_f32(a1);
+        v.z = lds_f32(a2);
+        v.w = lds_f32(a3);
+        if (g.mute) {
+            if (g.mute & 1) v.x = 0.f;
+            if (g.mute & 2) v.y = 0.f;
+            if (g.mute & 4) v.z = 0.f;
+            if (g.mute & 8) v.w = 0.f;
+        }
+        __stcs(dst, v);
+        dst += g.T2;
+        a0 += g.step; a1 += g.step; a2 += g.step; a3 += g.step;
+    }
+}
 
 // ------------------------------------------------------------ long frame ---
 // One stereo (or mono: nch == 1) long block per call.  See file header.
-template <bool kStereo>
+template <int kMode>
 __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long f,
                                            int cb, int nch, bool store, bool more, long long fnext,
-                                           const float (&w4)[4])
+                                           const float (&w4)[4], GroupCtx &grp)
 {
+    constexpr bool kStereo = kMode == kModeStereo;
     constexpr float pre_re[30] = {NQ_PRE30_RE};
     constexpr float pre_im[30] = {NQ_PRE30_IM};
     constexpr float post_re[16] = {NQ_POST16_RE};
@@ -116,6 +178,10 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
         }
     }
     idft30(g);
+    if (kMode == kModeGroup && grp.pending) {   // the group's previous store pass reads ws.x of every warp
+        group_sync(grp);
+        grp.pending = false;
+    }
     {
         const float2 *tw = tb.t_long + n2 * kXRowF2;
         float2 *dst = ws.x + c1 * kXChanF2 + n2 * kXRowF2;
@@ -127,7 +193,7 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
     if (more && lane == 0) {
         mbar_expect_tx(&ws.bar, nch * kFrame * 4);
         for (int ch = 0; ch < nch; ch++) {
-            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.C * kFrame) + (cb + ch) * kFrame;
+            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + (cb + ch) * kFrame;
             tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
         }
     }
@@ -181,6 +247,18 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
 #pragma unroll
             for (int k2 = 0; k2 < 15; k2++)
                 __stcs(dst + 30 + k1 + 30 * k2, make_float4(E[0][k2], E[1][k2], O[0][k2], O[1][k2]));
+        } else if (kMode == kModeGroup) {
+            // the frame as a [960][2] plane in the (now idle) transpose buffer; column 1 of a mono stream is unused
+            float4 *pl = reinterpret_cast<float4 *>(ws.x);
+            if (nch == 2) {
+                pl[29 - k1] = make_float4(H0[0], H0[1], H1[0], H1[1]);
+#pragma unroll
+                for (int k2 = 0; k2 < 15; k2++) pl[30 + k1 + 30 * k2] = make_float4(E[0][k2], E[1][k2], O[0][k2], O[1][k2]);
+            } else {
+                pl[29 - k1] = make_float4(H0[0], 0.f, H1[0], 0.f);
+#pragma unroll
+                for (int k2 = 0; k2 < 15; k2++) pl[30 + k1 + 30 * k2] = make_float4(E[0][k2], 0.f, O[0][k2], 0.f);
+            }
         } else {
             // generic channel count: channel pair (cb, cb+1) of an interleaved [n][C] frame
             float *dst = p.pcm + f * kFrame * p.C + cb;
@@ -221,10 +299,11 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
 // ------------------------------------------------------ transient frame ----
 // 8 short blocks per channel (N = 240, N2 = 120, N4 = 60), sub-block b uses
 // coefficients X[b + 8j] (celt_decoder_clean.c:292-300).
-template <bool kStereo>
+template <int kMode>
 __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long f,
-                                            int cb, int nch, bool store, bool more, long long fnext)
+                                            int cb, int nch, bool store, bool more, long long fnext, GroupCtx &grp)
 {
+    constexpr bool kStereo = kMode == kModeStereo;
     constexpr float pre_re[30] = {NQ_PRE30_RE};
     constexpr float pre_im[30] = {NQ_PRE30_IM};
 
@@ -263,9 +342,13 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
     if (more && lane == 0) {
         mbar_expect_tx(&ws.bar, nch * kFrame * 4);
         for (int ch = 0; ch < nch; ch++) {
-            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.C * kFrame) + (cb + ch) * kFrame;
+            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + (cb + ch) * kFrame;
             tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
         }
+    }
+    if (kMode == kModeGroup && grp.pending) {   // see long_frame
+        group_sync(grp);
+        grp.pending = false;
     }
     // window + overlap-add against the previous sub-block's raw tail
     float *stage = reinterpret_cast<float *>(ws.x);   // [n][2] interleaved
@@ -288,7 +371,7 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
             ws.tail[c * kHalfOvl + 59 - m] = tl[k1];          // y_7[60 + (59-m)]
         }
     }
-    if (store) {
+    if (store && kMode != kModeGroup) {   // group mode: `stage` IS the stream's plane, stored by the group
         if (kStereo) {
             const float4 *s4 = reinterpret_cast<const float4 *>(stage);
             float4 *dst = reinterpret_cast<float4 *>(p.pcm + f * (kFrame * 2));
@@ -311,13 +394,18 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
 }
 
 // ----------------------------------------------------------- fast kernel ---
-template <bool kStereo>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) celt_synth_kernel(const __grid_constant__ SynthParams p)
+// kWarps = warps per CTA: 14 (what shared memory allows), or 12 for group shapes that cannot use
+// more than 12 anyway -- three warps per scheduler instead of four lifts the register cap from
+// 128 to 168 per thread, which the group variant needs to stay out of local memory.
+template <int kMode, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid_constant__ SynthParams p)
 {
+    constexpr bool kStereo = kMode == kModeStereo;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastTables &tb = *reinterpret_cast<FastTables *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem &ws = reinterpret_cast<WarpSmem *>(smem_raw + sizeof(FastTables))[warp];
+    WarpSmem *wsmem = reinterpret_cast<WarpSmem *>(smem_raw + sizeof(FastTables));
+    WarpSmem &ws = wsmem[warp];
 
     {
         const float *src = reinterpret_cast<const float *>(p.tables);
@@ -342,14 +430,61 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) celt_synth_kernel(const 
         w4[3] = tb.window[61 + 2 * k1];
     }
 
-    const long long total_warps = (long long)gridDim.x * kWarpsPerCta;
-    const long long nitems = p.nruns * p.npairs;
+    // Work items.  Stereo / direct: one warp per (run, channel pair).  Group: the CTA holds
+    // kWarpsPerCta / nstreams groups, a group owns a run, warp `slot` of the group owns stream `slot`.
+    long long item, item_stride, nitems;
+    int slot = 0;
+    GroupCtx grp;
+    grp.pending = false;
+    if (kMode == kModeGroup) {
+        const int W = p.nstreams, G = kWarps / W;
+        const int gi = warp / W;
+        slot = warp - gi * W;
+        if (gi >= G) return;   // spare warps (no block-wide barrier below this point)
+        const int tg = slot * 32 + lane, C = p.C;
+        grp.T = W * 32;
+        grp.bar_id = 1 + gi;
+        grp.T2 = p.store_threads;
+        grp.q0 = tg;
+        grp.step = (uint32_t)(4 * grp.T2 / C) * 8u;
+        grp.niter = tg < grp.T2 ? ((kFrame / 4) * C - tg + grp.T2 - 1) / grp.T2 : 0;
+        grp.mute = 0;
+        int n = (4 * tg) / C, c = (4 * tg) % C;
+        const uint32_t planes = smem_u32(wsmem + gi * W) + kPlaneOffFloats * 4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned sc = p.chan_src[c];
+            if (sc == 0xffffu) grp.mute |= 1u << j;
+            grp.src[j] = sc == 0xffffu ? planes : planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + (sc & 1) * 4 + n * 8;
+            if (++c == C) { c = 0; n++; }
+        }
+        item = (long long)blockIdx.x * G + gi;
+        item_stride = (long long)gridDim.x * G;
+        nitems = p.nruns;
+    } else {
+        item = (long long)blockIdx.x * kWarps + warp;
+        item_stride = (long long)gridDim.x * kWarps;
+        nitems = p.nruns * p.npairs;
+    }
     uint32_t phase = 0;
-    for (long long item = (long long)blockIdx.x * kWarpsPerCta + warp; item < nitems; item += total_warps) {
-        const long long run = kStereo ? item : item / p.npairs;
-        const int pair = kStereo ? 0 : int(item - run * p.npairs);
-        const int cb = 2 * pair;
-        const int nch = kStereo ? 2 : (p.C - cb >= 2 ? 2 : 1);
+    for (; item < nitems; item += item_stride) {
+        long long run;
+        int cb, nch, flag_col, halo_bit;
+        if (kMode == kModeGroup) {
+            const StreamDesc sd = p.streams[slot];
+            run = item;
+            cb = sd.row;
+            nch = sd.nch;
+            flag_col = sd.flag_col;
+            halo_bit = p.flag_per_stream ? slot : 0;
+        } else {
+            run = kStereo ? item : item / p.npairs;
+            const int pair = kStereo ? 0 : int(item - run * p.npairs);
+            cb = 2 * pair;
+            nch = kStereo ? 2 : (p.D - cb >= 2 ? 2 : 1);
+            flag_col = p.flag_per_stream ? pair : 0;
+            halo_bit = p.flag_per_stream ? (pair & 31) : 0;
+        }
         const long long f0 = run * p.frames_per_run;
         const long long f1 = (f0 + p.frames_per_run < p.nframes) ? f0 + p.frames_per_run : p.nframes;
         // A run that does not open the batch (or a batch with a halo frame)
@@ -363,22 +498,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) celt_synth_kernel(const 
         }
         __syncwarp();
         long long f = warm ? f0 - 1 : f0;
-        const uint8_t *flags = p.transient + (p.flag_per_pair ? pair : 0);
+        const uint8_t *flags = p.transient + flag_col;
         if (lane == 0) {
             mbar_expect_tx(&ws.bar, nch * kFrame * 4);
             for (int ch = 0; ch < nch; ch++) {
-                const float *src = (f < 0 ? p.halo_coef : p.coef + f * p.C * kFrame) + (cb + ch) * kFrame;
+                const float *src = (f < 0 ? p.halo_coef : p.coef + f * p.D * kFrame) + (cb + ch) * kFrame;
                 tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
             }
         }
-        int is_tr = f < 0 ? p.halo_transient : flags[f * p.flag_stride];
+        int is_tr = f < 0 ? ((p.halo_transient >> halo_bit) & 1) : flags[f * p.flag_stride];
         for (; f < f1; f++) {
             const bool more = f + 1 < f1;
             const int next_tr = more ? flags[(f + 1) * p.flag_stride] : 0;
             while (!mbar_try_wait(&ws.bar, phase)) {}
             phase ^= 1;
-            if (!is_tr) long_frame<kStereo>(p, tb, ws, lane, f, cb, nch, f >= f0, more, f + 1, w4);
-            else short_frame<kStereo>(p, tb, ws, lane, f, cb, nch, f >= f0, more, f + 1);
+            const bool store = f >= f0;
+            if (!is_tr) long_frame<kMode>(p, tb, ws, lane, f, cb, nch, store, more, f + 1, w4, grp);
+            else short_frame<kMode>(p, tb, ws, lane, f, cb, nch, store, more, f + 1, grp);
+            if (kMode == kModeGroup && store) {
+                group_sync(grp);   // every stream's plane of frame f is complete
+                group_store_frame(grp, p.pcm + f * kFrame * p.C);
+                grp.pending = true;   // ... and must stay intact until the whole group is through this pass
+            }
             is_tr = next_tr;
         }
         __syncwarp();
@@ -390,29 +531,68 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) celt_synth_kernel(const 
         }
         __syncwarp();
     }
+    // (a pending group barrier needs no partner at exit: nobody overwrites a plane any more)
+}
+
+// Warps per CTA of the group variant for this group width (see celt_synth_kernel): 12 unless only
+// 14 fits the group at all or doubles the groups of the CTA (7, 13 or 14 streams).
+static int group_cta_warps(int nstreams) { return nstreams == 7 || nstreams > 12 ? kWarpsPerCta : 12; }
+
+int groups_per_cta(int nstreams)
+{
+    return nstreams >= 1 && nstreams <= kMaxGroupStreams ? group_cta_warps(nstreams) / nstreams : 0;
+}
+
+// Threads of a group that take part in the store pass: the largest T2 <= 32*nstreams with
+// 4*T2 a multiple of C (see GroupCtx); 0 if that leaves less than half of the group busy.
+int group_store_threads(int C, int nstreams)
+{
+    int g = C % 4 == 0 ? 4 : (C % 2 == 0 ? 2 : 1);
+    const int m = C / g, T = 32 * nstreams;
+    const int T2 = (T / m) * m;
+    return 2 * T2 >= T ? T2 : 0;
+}
+
+int synth_mode(int D, int C, int nstreams, bool identity_map)
+{
+    if (D == 2 && C == 2 && nstreams == 1 && identity_map) return kModeStereo;
+    if (nstreams <= kMaxGroupStreams && group_store_threads(C, nstreams) > 0) return kModeGroup;
+    return kModeDirect;
 }
 
 cudaError_t prepare_kernels()
 {
-    cudaError_t e = cudaFuncSetAttribute(celt_synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)fast_kernel_smem_bytes());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(celt_synth_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)fast_kernel_smem_bytes());
+    const int smem = (int)fast_kernel_smem_bytes();
+    const void *kernels[] = {(const void *)celt_synth_kernel<kModeStereo, kWarpsPerCta>,
+                             (const void *)celt_synth_kernel<kModeGroup, kWarpsPerCta>,
+                             (const void *)celt_synth_kernel<kModeGroup, 12>,
+                             (const void *)celt_synth_kernel<kModeDirect, kWarpsPerCta>};
+    for (const void *k : kernels) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
-cudaError_t launch_synth(const SynthParams &p, int num_sms, cudaStream_t stream, int *launched_ctas)
+cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream_t stream, int *launched_ctas)
 {
-    const long long nitems = p.nruns * p.npairs;
-    long long ctas = (nitems + kWarpsPerCta - 1) / kWarpsPerCta;
+    long long per_cta = kWarpsPerCta, nitems = p.nruns * p.npairs;
+    int warps = kWarpsPerCta;
+    if (mode == kModeGroup) {
+        per_cta = groups_per_cta(p.nstreams);
+        nitems = p.nruns;
+        warps = group_cta_warps(p.nstreams);
+    }
+    long long ctas = (nitems + per_cta - 1) / per_cta;
     if (ctas > num_sms) ctas = num_sms;   // persistent: one CTA per SM, warps stride over the items
     if (ctas < 1) ctas = 1;
     if (launched_ctas) *launched_ctas = (int)ctas;
-    const size_t smem = fast_kernel_smem_bytes();
-    if (p.C == 2)
-        celt_synth_kernel<true><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
-    else
-        celt_synth_kernel<false><<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+    const size_t smem = sizeof(FastTables) + (size_t)warps * sizeof(WarpSmem);
+    const unsigned grid = (unsigned)ctas, block = warps * 32;
+    if (mode == kModeStereo) celt_synth_kernel<kModeStereo, kWarpsPerCta><<<grid, block, smem, stream>>>(p);
+    else if (mode == kModeGroup && warps == 12) celt_synth_kernel<kModeGroup, 12><<<grid, block, smem, stream>>>(p);
+    else if (mode == kModeGroup) celt_synth_kernel<kModeGroup, kWarpsPerCta><<<grid, block, smem, stream>>>(p);
+    else celt_synth_kernel<kModeDirect, kWarpsPerCta><<<grid, block, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -33,22 +33,46 @@ struct GenericTables {
     float window[kOverlap];
 };
 
+// How the fast kernel is specialised (template parameter):
+//   kModeStereo  D = C = 2, one warp per run, float4 {L,R,L,R} stores straight from registers;
+//   kModeGroup   any channel layout with <= kMaxGroupStreams streams: a GROUP of warps (one per
+//                stream = one coupled pair or one mono channel) walks a run together; every warp
+//                leaves its frame as a [960][2] plane in shared memory and the group then writes
+//                the interleaved [960][C] output frame with contiguous float4 stores, gathering
+//                output channel c from decoded channel mapping[c] (opus_multistream_decoder.c:260-299);
+//   kModeDirect  more streams than a CTA has warps: channel pairs, scattered stores (slow, rare).
+constexpr int kModeStereo = 0, kModeGroup = 1, kModeDirect = 2;
+constexpr int kMaxGroupStreams = kWarpsPerCta;
+constexpr int kMaxChannels = 255;
+
+struct StreamDesc {
+    uint8_t nch;        // 2: coupled stream, 1: mono stream
+    uint8_t row;        // first decoded channel (coefficient row inside a frame)
+    uint8_t flag_col;   // column of the transient flag inside a frame's flag record
+    uint8_t pad_;
+};
+
 struct SynthParams {
-    const float *coef;          // [nframes][C][960]
+    const float *coef;          // [nframes][D][960]
     const uint8_t *transient;   // [nframes][flag_stride]
-    const float *tail_in;       // [C][60] or nullptr
-    const float *halo_coef;     // [C][960] coefficients of frame -1, or nullptr
+    const float *tail_in;       // [D][60] or nullptr
+    const float *halo_coef;     // [D][960] coefficients of frame -1, or nullptr
     float *pcm;                 // [nframes*960][C]
-    float *tail_out;            // [C][60] or nullptr
+    float *tail_out;            // [D][60] or nullptr
     const FastTables *tables;
     long long nframes;
     long long frames_per_run;
     long long nruns;
-    int C;
-    int npairs;
-    int halo_transient;
-    int flag_stride;            // bytes between the flags of consecutive frames
-    int flag_per_pair;          // 0: every channel pair reads column 0; 1: pair p reads column p
+    int D;                      // decoded channels per frame (coefficient rows)
+    int C;                      // output channels (pcm row width); == D without a channel mapping
+    int npairs;                 // kModeDirect: channel pairs per frame
+    int nstreams;               // kModeGroup: warps per group
+    int store_threads;          // kModeGroup: threads of a group in the store pass (group_store_threads())
+    int halo_transient;         // flag(s) of the halo frame: bit s = stream s (bit 0 for everybody if !flag_per_stream)
+    int flag_stride;            // bytes between the flag records of consecutive frames
+    int flag_per_stream;        // 0: every stream reads column 0; 1: stream / pair s reads column s
+    StreamDesc streams[kMaxGroupStreams];
+    uint16_t chan_src[kMaxChannels + 1];   // kModeGroup: output channel c <- (stream slot << 1 | sub), 0xffff = silent
 };
 
 // One clt_mdct_backward call (mdct.c:267): device pointers.
@@ -61,7 +85,10 @@ struct MdctCall {
 };
 
 size_t fast_kernel_smem_bytes();
-cudaError_t launch_synth(const SynthParams &p, int num_sms, cudaStream_t stream, int *launched_ctas);
+int synth_mode(int D, int C, int nstreams, bool identity_map);
+int groups_per_cta(int nstreams);
+int group_store_threads(int C, int nstreams);
+cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream_t stream, int *launched_ctas);
 cudaError_t launch_mdct_generic(const MdctCall *d_calls, int ncalls, const GenericTables *d_tables, cudaStream_t stream);
 cudaError_t prepare_kernels();
 

@@ -159,6 +159,73 @@ def test_synth_batch_many_runs_vs_oracle(synth, C, p_tr):
     assert_parity(want_tail, tail, "tail")
 
 
+# ---- BASELINE config 4: Opus multistream layouts, interleave fused into the store pass ----
+def ms_oracle(coef, tr, streams, coupled, mapping, tail_in=None):
+    """Per-stream compute_inv_mdcts (oracle) + the channel routing of
+    opus_multistream_decoder.c:260-299 / opus_multistream.c:57-91, in numpy."""
+    nframes, D, _ = coef.shape
+    dec = np.zeros((nframes * 960, D), np.float32)
+    tails = np.zeros((D, 60), np.float32)
+    for s in range(streams):
+        rows = [2 * s, 2 * s + 1] if s < coupled else [s + coupled]
+        ti = None if tail_in is None else np.ascontiguousarray(tail_in[rows])
+        pcm, tl, _ = port.synth_batch(np.ascontiguousarray(coef[:, rows]), np.ascontiguousarray(tr[:, s]), ti, nthreads=4)
+        dec[:, rows] = pcm
+        tails[rows] = tl
+    out = np.zeros((nframes * 960, len(mapping)), np.float32)
+    for c, d in enumerate(mapping):
+        if d != 255:
+            out[:, c] = dec[:, d]
+    return out, tails
+
+
+MS_LAYOUTS = {
+    # (streams, coupled, mapping): the Vorbis-order surround layouts of opus_multistream_encoder.c:60-69
+    "mono": (1, 0, [0]),
+    "stereo_mapped": (1, 1, [1, 0]),
+    "surround_5.1": (4, 2, [0, 4, 1, 2, 3, 5]),
+    "surround_7.1": (5, 3, [0, 6, 1, 2, 3, 4, 5, 7]),
+    "dual_mono_muted_dup": (3, 1, [2, 255, 0, 0, 1, 3, 3]),
+    "fourteen_mono": (14, 0, list(range(14))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MS_LAYOUTS))
+def test_multistream_layouts_fused_interleave(synth, name):
+    import torch
+    streams, coupled, mapping = MS_LAYOUTS[name]
+    D = streams + coupled
+    rng = np.random.default_rng(len(name))
+    nframes = 700
+    coef, _ = rand_batch(rng, nframes, D, 0.0)
+    tr = (rng.uniform(size=(nframes, streams)) < 0.15).astype(np.uint8)
+    tail_in = (rng.standard_normal((D, 60)) * 100).astype(np.float32)
+    want, want_tail = ms_oracle(coef, tr, streams, coupled, mapping, tail_in)
+    d_coef, d_tr = torch.from_numpy(coef).cuda(), torch.from_numpy(tr).cuda()
+    pcm, tail = synth.synth_batch_ms_torch(d_coef, d_tr, streams, coupled, mapping, tail_in=torch.from_numpy(tail_in).cuda())
+    torch.cuda.synchronize()
+    assert_parity(want, pcm.cpu().numpy(), name)
+    assert_parity(want_tail, tail.cpu().numpy(), name + " tail")
+    # a shard that starts mid-stream from a halo frame is bit-identical to the unsharded run
+    cut = 333
+    part, _ = synth.synth_batch_ms_torch(d_coef[cut:].contiguous(), d_tr[cut:].contiguous(), streams, coupled, mapping,
+                                         halo_coef=d_coef[cut - 1].contiguous(), halo_transient=tr[cut - 1])
+    torch.cuda.synchronize()
+    assert torch.equal(part, pcm[cut * 960:])
+
+
+def test_multistream_rejects_bad_layouts(synth):
+    import torch
+    coef = torch.zeros((4, 3, 960), device="cuda")
+    tr = torch.zeros((4, 2), dtype=torch.uint8, device="cuda")
+    with pytest.raises(nq.NqError):
+        synth.synth_batch_ms_torch(coef, tr, 2, 1, [0, 1, 3])        # decoded channel 3 does not exist
+    with pytest.raises(nq.NqError) as e:
+        synth.synth_batch_ms_torch(torch.zeros((4, 15, 960), device="cuda"),
+                                   torch.zeros((4, 15), dtype=torch.uint8, device="cuda"), 15, 0, list(range(15)))
+    assert e.value.code == -5
+
+
 def test_edge_cases_and_error_codes(synth):
     rng = np.random.default_rng(5)
     # empty batch: tail passes through

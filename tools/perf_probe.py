@@ -27,8 +27,15 @@ def run(synth, frames, C, p_tr, steps=5):
                 Mframes_per_s=round(frames / ms / 1e3, 2), frac_of_6527=round(gbs / 6527.5, 3))
 
 if __name__ == "__main__":
+    # --case frames,C,p_transient[,steps] (repeatable): run only these (used under ncu)
+    cases = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--case=")]
     with nq.CeltSynth(0) as s:
+        for c in cases:
+            fr, C, p, *st = c.split(",")
+            print(json.dumps(run(s, int(fr), int(C), float(p), int(st[0]) if st else 5)), flush=True)
+        if cases:
+            sys.exit(0)
         for frames, C, p in [(2_000_000, 2, 0.0), (2_000_000, 2, 0.028), (2_000_000, 2, 0.2), (2_000_000, 2, 1.0),
-                             (4_000_000, 1, 0.028), (500_000, 8, 0.028), (1_300_000, 3, 0.028),
+                             (4_000_000, 1, 0.028), (500_000, 8, 0.028), (500_000, 8, 0.2), (1_300_000, 3, 0.028), (700_000, 6, 0.028),
                              (20_000, 2, 0.028), (2_000, 2, 0.028)]:
             print(json.dumps(run(s, frames, C, p)), flush=True)
