@@ -131,6 +131,46 @@ NQ_API int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, co
                                          int64_t nframes, int channels, int streams, int coupled_streams,
                                          const unsigned char *mapping, void *stream);
 
+/* ---- post stage: pitch post-filter + de-emphasis ---
+ * What celt_decode_with_ec does to out_syn after compute_inv_mdcts: comb_filter
+ * twice (celt_decoder_clean.c:658-670, celt/celt.c:114-172), the parameter
+ * hand-over (:672-683) and deemphasis (:723, :192-256), which also scales to
+ * [-1, 1] and interleaves.  Side information per frame per stream, produced by
+ * phase 1 (the entropy decoder): */
+typedef struct nq_celt_post_frame {
+    int32_t N;          /* samples per channel of the frame: 120 << LM                       */
+    int32_t pitch[3];   /* postfilter_period_old, postfilter_period, postfilter_pitch (:436) */
+    float gain[3];      /* ..._gain_old, ..._gain, postfilter_gain                           */
+    int32_t tapset[3];  /* ..._tapset_old, ..._tapset, postfilter_tapset                     */
+} nq_celt_post_frame;   /* i.e. [0] -> [1] fades over samples [0,120), [1] -> [2] over [120,240), [2] from there on */
+#define NQ_CELT_POST_HISTORY 1026   /* COMBFILTER_MAXPERIOD + 2 (celt.h:187) filtered samples per channel */
+
+/* In place on the buffer the synthesis wrote: pcm [nsamples][channels] holds
+ * celt_sig on entry and float PCM in [-1, 1] on return (nsamples = sum of N).
+ *   frames   [nframes][streams]  HOST pointer (40 bytes per stream-frame)
+ *   hist_*   [D][1026]           last filtered samples per decoded channel
+ *                                (the part of decode_mem the comb filter reads,
+ *                                celt_decoder_clean.c:92); NULL in = reset decoder
+ *   mem_*    [D]                 preemph_memD (celt_decoder_clean.c:90)
+ * pcm / hist / mem are device pointers.  mapping == NULL: one CELT decoder,
+ * channels = 1 or 2, streams = 1.  One warp per stream walks the frames in
+ * order (the filters are recurrences): parallel over streams, not over time. */
+NQ_API int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *frames,
+                                     const float *hist_in, const float *mem_in, float *hist_out, float *mem_out,
+                                     int64_t nframes, int channels, int streams, int coupled_streams,
+                                     const unsigned char *mapping, void *stream);
+
+/* Whole phase 2 on host buffers: coefficients + side info in, float PCM out
+ * (synthesis, channel mapping, post-filter, de-emphasis), chunks pipelined
+ * H2D / kernels / D2H.  Decoder state (tail [D][60], hist [D][1026], mem [D];
+ * NULL in = reset decoder, NULL out = discard) lets a stream be fed in pieces.
+ * 20 ms frames only (NQ_UNIMPLEMENTED otherwise). */
+NQ_API int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient,
+                                     const nq_celt_post_frame *frames, const float *tail_in, const float *hist_in,
+                                     const float *mem_in, float *pcm_out, float *tail_out, float *hist_out,
+                                     float *mem_out, int64_t nframes, int channels, int streams,
+                                     int coupled_streams, const unsigned char *mapping);
+
 /* Same as _host, frames sharded contiguously over `ndev` devices (devices[i]
  * = CUDA ordinal; NULL => 0..ndev-1) with one host thread + context per
  * device and NO device-to-device traffic: a shard that starts mid-stream

@@ -29,12 +29,18 @@ OVERLAP = 120
 MDCT_N = 1920
 
 NQ_OK = 0
+POST_HISTORY = 1026
+
+# nq_celt_post_frame (include/nq_celt_synth.h): the arguments of the two comb_filter calls of a
+# frame, celt_decoder_clean.c:660-669
+POST_FRAME_DTYPE = np.dtype([("N", np.int32), ("pitch", np.int32, 3), ("gain", np.float32, 3),
+                             ("tapset", np.int32, 3)])
 
 EXPORTED_SYMBOLS = [
     "nq_celt_ctx_create", "nq_celt_ctx_destroy", "nq_celt_strerror", "nq_celt_last_error",
     "nq_celt_device_count", "nq_celt_launch_count", "nq_celt_host_alloc", "nq_celt_host_free",
     "nq_celt_synth_batch_device", "nq_celt_synth_batch_device_ms", "nq_celt_synth_batch_host",
-    "nq_celt_synth_batch_host_multi",
+    "nq_celt_synth_batch_host_multi", "nq_celt_post_batch_device", "nq_celt_decode_batch_host",
     "nq_clt_mdct_backward", "nq_clt_mdct_backward_B1_C2", "nq_celt_mdct_backward_host",
     "nq_compute_inv_mdcts", "nq_opus_ifft_host", "processMDCTCuda", "processMDCTCudaB1C2", "cleanupCudaBuffers",
     "printCudaVersion", "nq_celt_debug_tables",
@@ -76,6 +82,9 @@ def load_library():
     L.nq_celt_synth_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int]
     L.nq_celt_synth_batch_device_ms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int,
                                                 vp, vp]
+    L.nq_celt_post_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.nq_celt_decode_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int,
+                                            C.c_int, vp]
     L.nq_celt_synth_batch_host_multi.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int]
     L.nq_clt_mdct_backward.argtypes = [vp, fp, fp, fp, C.c_int, C.c_int, C.c_int]
     L.nq_clt_mdct_backward.restype = None
@@ -281,6 +290,57 @@ class CeltSynth:
             C.c_void_p(0 if tail is None else tail.data_ptr()), nframes, ch, int(streams), int(coupled_streams),
             _vp(mp), C.c_void_p(st)))
         return pcm, tail
+
+
+    # -- post stage: comb_filter x2 + deemphasis, celt_decoder_clean.c:658-670, :723 ----------
+    def post_batch_torch(self, pcm, frames, hist_in=None, mem_in=None, streams=1, coupled_streams=None,
+                         mapping=None, want_state=True, stream=None):
+        """In place on pcm (cuda f32 [nsamples][channels], celt_sig in, PCM out).  frames: numpy
+        POST_FRAME_DTYPE [nframes] or [nframes][streams].  Returns (hist_out [D][1026], mem_out [D])."""
+        import torch
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous() and pcm.dim() == 2
+        ch = pcm.shape[1]
+        fr = np.ascontiguousarray(frames, POST_FRAME_DTYPE).reshape(-1, streams)
+        if coupled_streams is None:
+            coupled_streams = 1 if (mapping is None and ch == 2) else 0
+        D = streams + coupled_streams
+        assert int(fr["N"][:, 0].sum()) == pcm.shape[0], "sum of frame sizes must equal the sample count"
+        mp = None if mapping is None else np.ascontiguousarray(mapping, np.uint8)
+        hist = torch.empty((D, POST_HISTORY), dtype=torch.float32, device=pcm.device) if want_state else None
+        mem = torch.empty((D,), dtype=torch.float32, device=pcm.device) if want_state else None
+        st = (stream if stream is not None else torch.cuda.current_stream(pcm.device)).cuda_stream
+        if st == 0:
+            st = 1
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        self._check(self._L.nq_celt_post_batch_device(
+            self._h, ptr(pcm), _vp(fr), ptr(hist_in), ptr(mem_in), ptr(hist), ptr(mem), fr.shape[0], ch,
+            int(streams), int(coupled_streams), _vp(mp), C.c_void_p(st)))
+        return hist, mem
+
+    # -- whole phase 2 on host buffers ----------------------------------------------------------
+    def decode_batch(self, coef, transient, frames, state=None, streams=1, coupled_streams=None, mapping=None):
+        """coef [nframes][D][960] f32, transient [nframes] or [nframes][streams] u8, frames
+        POST_FRAME_DTYPE [nframes] or [nframes][streams]; state = (tail [D][60], hist [D][1026],
+        mem [D]) or None for a reset decoder.  Returns (pcm [nframes*960][channels], new state)."""
+        _f32c(coef, "coef")
+        nframes, D, n = coef.shape
+        if coupled_streams is None:
+            coupled_streams = 1 if (mapping is None and D == 2) else 0
+        assert n == FRAME and D == streams + coupled_streams
+        mp = None if mapping is None else np.ascontiguousarray(mapping, np.uint8)
+        ch = D if mp is None else mp.size
+        tr = np.ascontiguousarray(transient, np.uint8).reshape(nframes, -1)
+        assert tr.shape[1] == (streams if mp is not None else 1)
+        fr = np.ascontiguousarray(frames, POST_FRAME_DTYPE).reshape(nframes, streams)
+        ti, hi, mi = (None, None, None) if state is None else [np.ascontiguousarray(a, np.float32) for a in state]
+        pcm = np.empty((nframes * FRAME, ch), np.float32)
+        to = np.zeros((D, HALF_OVERLAP), np.float32)
+        ho = np.zeros((D, POST_HISTORY), np.float32)
+        mo = np.zeros((D,), np.float32)
+        self._check(self._L.nq_celt_decode_batch_host(self._h, _vp(coef), _vp(tr), _vp(fr), _vp(ti), _vp(hi), _vp(mi),
+                                                      _vp(pcm), _vp(to), _vp(ho), _vp(mo), nframes, ch, int(streams),
+                                                      int(coupled_streams), _vp(mp)))
+        return pcm, (to, ho, mo)
 
 
 def synth_batch_multi_gpu(coef: np.ndarray, transient: np.ndarray, tail_in=None, devices=None):

@@ -90,9 +90,23 @@ struct nq_celt_ctx {
     uint8_t *d_flags[kSlots] = {};
     size_t slot_frames_cap = 0;
     int slot_C_cap = 0;
+    size_t slot_in_cap = 0, slot_out_cap = 0, slot_flag_cap = 0;   // bytes
     float *d_tail[2] = {};
     float *d_halo = nullptr;
     int tail_C_cap = 0;
+    // post stage: side info + jobs per slot, filter state ping-pong between chunks
+    PostFrame *d_pframes[kSlots] = {};
+    size_t pframes_cap[kSlots] = {};
+    PostJob *d_pjobs[kSlots] = {};
+    int pjobs_cap[kSlots] = {};
+    float *d_hist[2] = {};
+    float *d_mem[2] = {};
+    int post_rows_cap = 0;
+    // ... and for the device-pointer post entry
+    PostFrame *d_pframes_dev = nullptr;
+    size_t pframes_dev_cap = 0;
+    PostJob *d_pjobs_dev = nullptr;
+    int pjobs_dev_cap = 0;
     // scratch for the single-call entries
     float *d_call_buf = nullptr;
     size_t call_buf_cap = 0;
@@ -325,7 +339,7 @@ int nq_celt_ctx_create(int device, nq_celt_ctx **out)
         return bail(NQ_INTERNAL_ERROR);
     }
     ctx->num_sms = prop.multiProcessorCount;
-    if (prepare_kernels() != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    if (prepare_kernels() != cudaSuccess || prepare_post_kernel() != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
     for (int s = 0; s < nq_celt_ctx::kSlots; s++) {
         if (cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
@@ -355,6 +369,10 @@ void nq_celt_ctx_destroy(nq_celt_ctx *ctx)
     cudaFree(ctx->d_tail[0]);
     cudaFree(ctx->d_tail[1]);
     cudaFree(ctx->d_halo);
+    for (int s = 0; s < nq_celt_ctx::kSlots; s++) { cudaFree(ctx->d_pframes[s]); cudaFree(ctx->d_pjobs[s]); }
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->d_hist[i]); cudaFree(ctx->d_mem[i]); }
+    cudaFree(ctx->d_pframes_dev);
+    cudaFree(ctx->d_pjobs_dev);
     cudaFree(ctx->d_call_buf);
     cudaFree(ctx->d_calls);
     cudaFree(ctx->d_fast);
@@ -424,72 +442,209 @@ int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, const uin
 
 namespace {
 
-// Host-pointer batch over [0, nframes) with an optional host halo frame.
+static_assert(sizeof(PostFrame) == sizeof(nq_celt_post_frame), "side-info record layout");
+
+// Post jobs of one contiguous frame range: adjacent output channels fed by the two channels of
+// one coupled stream share a warp; every other live channel gets its own; silent channels none.
+void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes, bool reset, std::vector<PostJob> *jobs)
+{
+    for (int c = 0; c < L.C;) {
+        const int d = L.mapping[c];
+        if (d == 255) { c++; continue; }
+        PostJob j;
+        memset(&j, 0, sizeof j);
+        j.sample0 = sample0;
+        j.frame0 = frame0;
+        j.nframes = nframes;
+        j.ch0 = c;
+        j.state_row = d;
+        j.reset = reset ? 1 : 0;
+        if (d < 2 * L.coupled && (d & 1) == 0 && c + 1 < L.C && L.mapping[c + 1] == d + 1) {
+            j.nch = 2;
+            j.stream_col = d >> 1;
+            c += 2;
+        } else {
+            j.nch = 1;
+            j.stream_col = d < 2 * L.coupled ? d >> 1 : d - L.coupled;
+            c += 1;
+        }
+        jobs->push_back(j);
+    }
+}
+
+int enqueue_post(nq_celt_ctx *ctx, const Layout &L, float *pcm, const PostFrame *d_frames, const PostJob *d_jobs, int njobs,
+                 const float *hist_in, const float *mem_in, float *hist_out, float *mem_out, cudaStream_t stream)
+{
+    PostParams p;
+    memset(&p, 0, sizeof p);
+    p.pcm = pcm;
+    p.frames = d_frames;
+    p.jobs = d_jobs;
+    p.window = ctx->d_gen->window;
+    p.hist_in = hist_in;
+    p.mem_in = mem_in;
+    p.hist_out = hist_out;
+    p.mem_out = mem_out;
+    p.C = L.C;
+    p.frame_stride = L.streams;
+    NQ_CUDA(ctx, launch_post(p, njobs, stream));
+    ctx->launches++;
+    return NQ_OK;
+}
+
+template <class T>
+int grow(nq_celt_ctx *ctx, T **buf, size_t *cap, size_t need_bytes, const char *what)
+{
+    if (need_bytes <= *cap) return NQ_OK;
+    cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    if (cudaMalloc(buf, need_bytes) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "%s (%zu bytes)", what, need_bytes);
+    *cap = need_bytes;
+    return NQ_OK;
+}
+
+// Host-pointer batch over [0, nframes): chunks are pipelined H2D / synthesis (/ post stage) / D2H
+// on the context's slot streams.  `halo_coef` (+ flags): optional host halo frame of a shard that
+// starts mid-stream.  `pframes` != NULL adds the post stage (all frames must be 20 ms frames).
+struct HostState {
+    const float *tail_in = nullptr;    // [D][60]
+    float *tail_out = nullptr;
+    const float *hist_in = nullptr;    // [D][1026]
+    const float *mem_in = nullptr;     // [D]
+    float *hist_out = nullptr;
+    float *mem_out = nullptr;
+};
+
+int host_range(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8_t *transient,
+               const nq_celt_post_frame *pframes, const HostState &st, const float *halo_coef, unsigned halo_bits,
+               float *pcm_out, long long nframes)
+{
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    constexpr int S = nq_celt_ctx::kSlots;
+    const size_t in_row = (size_t)L.D * kFrame, out_row = (size_t)L.C * kFrame;
+    const size_t flag_row = L.per_stream_flags ? (size_t)L.streams : 1;
+    // chunk size: ~64 MB of coefficients per slot, enough frames to fill the GPU
+    long long chunk = (long long)((64u << 20) / (in_row * sizeof(float)));
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > nframes) chunk = nframes;
+    {
+        bool need = false;
+        for (int s = 0; s < S; s++)
+            need = need || !ctx->d_in[s] || !ctx->d_out[s] || !ctx->d_flags[s];
+        need = need || chunk * in_row * sizeof(float) > ctx->slot_in_cap || chunk * out_row * sizeof(float) > ctx->slot_out_cap ||
+               chunk * flag_row > ctx->slot_flag_cap;
+        if (need) {
+            for (int s = 0; s < S; s++) {
+                NQ_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+                cudaFree(ctx->d_in[s]); cudaFree(ctx->d_out[s]); cudaFree(ctx->d_flags[s]);
+                ctx->d_in[s] = ctx->d_out[s] = nullptr; ctx->d_flags[s] = nullptr;
+            }
+            ctx->slot_in_cap = ctx->slot_out_cap = ctx->slot_flag_cap = 0;
+            for (int s = 0; s < S; s++) {
+                if (cudaMalloc(&ctx->d_in[s], chunk * in_row * sizeof(float)) != cudaSuccess ||
+                    cudaMalloc(&ctx->d_out[s], chunk * out_row * sizeof(float)) != cudaSuccess ||
+                    cudaMalloc(&ctx->d_flags[s], chunk * flag_row) != cudaSuccess)
+                    return fail(ctx, NQ_ALLOC_FAIL, "device scratch for %lld frames x %d channels", chunk, L.D);
+            }
+            ctx->slot_in_cap = chunk * in_row * sizeof(float);
+            ctx->slot_out_cap = chunk * out_row * sizeof(float);
+            ctx->slot_flag_cap = chunk * flag_row;
+        }
+    }
+    if (L.D > ctx->tail_C_cap) {
+        cudaFree(ctx->d_tail[0]); cudaFree(ctx->d_tail[1]); cudaFree(ctx->d_halo);
+        ctx->d_tail[0] = ctx->d_tail[1] = ctx->d_halo = nullptr;
+        ctx->tail_C_cap = 0;
+        if (cudaMalloc(&ctx->d_tail[0], sizeof(float) * L.D * kHalfOvl) != cudaSuccess ||
+            cudaMalloc(&ctx->d_tail[1], sizeof(float) * L.D * kHalfOvl) != cudaSuccess ||
+            cudaMalloc(&ctx->d_halo, sizeof(float) * in_row) != cudaSuccess)
+            return fail(ctx, NQ_ALLOC_FAIL, "device tail buffers");
+        ctx->tail_C_cap = L.D;
+    }
+    if (pframes && L.D > ctx->post_rows_cap) {
+        for (int i = 0; i < 2; i++) {
+            cudaFree(ctx->d_hist[i]); cudaFree(ctx->d_mem[i]);
+            ctx->d_hist[i] = ctx->d_mem[i] = nullptr;
+        }
+        ctx->post_rows_cap = 0;
+        for (int i = 0; i < 2; i++)
+            if (cudaMalloc(&ctx->d_hist[i], sizeof(float) * L.D * kPostHist) != cudaSuccess ||
+                cudaMalloc(&ctx->d_mem[i], sizeof(float) * L.D) != cudaSuccess)
+                return fail(ctx, NQ_ALLOC_FAIL, "device post-filter state");
+        ctx->post_rows_cap = L.D;
+    }
+    const size_t tail_bytes = sizeof(float) * L.D * kHalfOvl;
+    const size_t hist_bytes = sizeof(float) * L.D * kPostHist, mem_bytes = sizeof(float) * L.D;
+    // chunk i reads its initial state from buffer (i+1)&1 and leaves its final state in buffer i&1
+    const bool use_halo = !st.tail_in && halo_coef;
+    cudaStream_t s0 = ctx->slot_stream[0];
+    if (st.tail_in) NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_tail[1], st.tail_in, tail_bytes, cudaMemcpyHostToDevice, s0));
+    else NQ_CUDA(ctx, cudaMemsetAsync(ctx->d_tail[1], 0, tail_bytes, s0));
+    if (use_halo) NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_halo, halo_coef, in_row * sizeof(float), cudaMemcpyHostToDevice, s0));
+    if (pframes) {
+        if (st.hist_in) NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_hist[1], st.hist_in, hist_bytes, cudaMemcpyHostToDevice, s0));
+        else NQ_CUDA(ctx, cudaMemsetAsync(ctx->d_hist[1], 0, hist_bytes, s0));
+        if (st.mem_in) NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_mem[1], st.mem_in, mem_bytes, cudaMemcpyHostToDevice, s0));
+        else NQ_CUDA(ctx, cudaMemsetAsync(ctx->d_mem[1], 0, mem_bytes, s0));
+    }
+
+    std::vector<PostJob> jobs;
+    const long long nchunks = (nframes + chunk - 1) / chunk;
+    for (long long i = 0; i < nchunks; i++) {
+        const int s = (int)(i % S);
+        cudaStream_t sst = ctx->slot_stream[s];
+        const long long f0 = i * chunk, n = (f0 + chunk <= nframes) ? chunk : nframes - f0;
+        NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_in[s], coef + f0 * in_row, n * in_row * sizeof(float), cudaMemcpyHostToDevice, sst));
+        NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags[s], transient + f0 * flag_row, (size_t)n * flag_row, cudaMemcpyHostToDevice, sst));
+        if (pframes) {
+            size_t cap = ctx->pframes_cap[s];
+            int rc = grow(ctx, &ctx->d_pframes[s], &cap, (size_t)n * L.streams * sizeof(PostFrame), "post side info");
+            ctx->pframes_cap[s] = cap;
+            if (rc != NQ_OK) return rc;
+            NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pframes[s], pframes + f0 * L.streams, (size_t)n * L.streams * sizeof(PostFrame),
+                                         cudaMemcpyHostToDevice, sst));
+        }
+        if (i > 0) NQ_CUDA(ctx, cudaStreamWaitEvent(sst, ctx->kernel_done[(i - 1) % S], 0));
+        const bool first_with_halo = (i == 0 && use_halo);
+        int rc = enqueue_synth(ctx, L, ctx->d_in[s], ctx->d_flags[s], first_with_halo ? nullptr : ctx->d_tail[(i + 1) & 1],
+                               first_with_halo ? ctx->d_halo : nullptr, halo_bits, ctx->d_out[s], ctx->d_tail[i & 1], n, sst);
+        if (rc != NQ_OK) return rc;
+        if (pframes) {
+            jobs.clear();
+            build_post_jobs(L, 0, 0, (int)n, false, &jobs);
+            if ((int)jobs.size() > ctx->pjobs_cap[s]) {
+                cudaFree(ctx->d_pjobs[s]);
+                ctx->d_pjobs[s] = nullptr;
+                ctx->pjobs_cap[s] = 0;
+                if (cudaMalloc(&ctx->d_pjobs[s], jobs.size() * sizeof(PostJob)) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "post jobs");
+                ctx->pjobs_cap[s] = (int)jobs.size();
+            }
+            NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pjobs[s], jobs.data(), jobs.size() * sizeof(PostJob), cudaMemcpyHostToDevice, sst));
+            rc = enqueue_post(ctx, L, ctx->d_out[s], ctx->d_pframes[s], ctx->d_pjobs[s], (int)jobs.size(), ctx->d_hist[(i + 1) & 1],
+                              ctx->d_mem[(i + 1) & 1], ctx->d_hist[i & 1], ctx->d_mem[i & 1], sst);
+            if (rc != NQ_OK) return rc;
+        }
+        NQ_CUDA(ctx, cudaEventRecord(ctx->kernel_done[s], sst));
+        NQ_CUDA(ctx, cudaMemcpyAsync(pcm_out + f0 * out_row, ctx->d_out[s], n * out_row * sizeof(float), cudaMemcpyDeviceToHost, sst));
+        if (i == nchunks - 1) {
+            if (st.tail_out) NQ_CUDA(ctx, cudaMemcpyAsync(st.tail_out, ctx->d_tail[i & 1], tail_bytes, cudaMemcpyDeviceToHost, sst));
+            if (pframes && st.hist_out) NQ_CUDA(ctx, cudaMemcpyAsync(st.hist_out, ctx->d_hist[i & 1], hist_bytes, cudaMemcpyDeviceToHost, sst));
+            if (pframes && st.mem_out) NQ_CUDA(ctx, cudaMemcpyAsync(st.mem_out, ctx->d_mem[i & 1], mem_bytes, cudaMemcpyDeviceToHost, sst));
+        }
+    }
+    for (int s = 0; s < S; s++) NQ_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+    return NQ_OK;
+}
+
 int synth_host_range(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const float *tail_in,
                      const float *halo_coef, int halo_transient, float *pcm_out, float *tail_out,
                      long long nframes, int C)
 {
-    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    constexpr int S = nq_celt_ctx::kSlots;
-    const size_t row = (size_t)C * kFrame;
-    // chunk size: ~64 MB of coefficients per slot, enough frames to fill the GPU
-    long long chunk = (long long)((64u << 20) / (row * sizeof(float)));
-    if (chunk < 1024) chunk = 1024;
-    if (chunk > nframes) chunk = nframes;
-    if ((size_t)chunk > ctx->slot_frames_cap || C > ctx->slot_C_cap) {
-        for (int s = 0; s < S; s++) {
-            NQ_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-            cudaFree(ctx->d_in[s]); cudaFree(ctx->d_out[s]); cudaFree(ctx->d_flags[s]);
-            ctx->d_in[s] = ctx->d_out[s] = nullptr; ctx->d_flags[s] = nullptr;
-        }
-        ctx->slot_frames_cap = 0;
-        for (int s = 0; s < S; s++) {
-            if (cudaMalloc(&ctx->d_in[s], chunk * row * sizeof(float)) != cudaSuccess ||
-                cudaMalloc(&ctx->d_out[s], chunk * row * sizeof(float)) != cudaSuccess ||
-                cudaMalloc(&ctx->d_flags[s], chunk) != cudaSuccess)
-                return fail(ctx, NQ_ALLOC_FAIL, "device scratch for %lld frames x %d channels", chunk, C);
-        }
-        ctx->slot_frames_cap = (size_t)chunk;
-        ctx->slot_C_cap = C;
-    }
-    if (C > ctx->tail_C_cap) {
-        cudaFree(ctx->d_tail[0]); cudaFree(ctx->d_tail[1]); cudaFree(ctx->d_halo);
-        ctx->d_tail[0] = ctx->d_tail[1] = ctx->d_halo = nullptr;
-        ctx->tail_C_cap = 0;
-        if (cudaMalloc(&ctx->d_tail[0], sizeof(float) * C * kHalfOvl) != cudaSuccess ||
-            cudaMalloc(&ctx->d_tail[1], sizeof(float) * C * kHalfOvl) != cudaSuccess ||
-            cudaMalloc(&ctx->d_halo, sizeof(float) * row) != cudaSuccess)
-            return fail(ctx, NQ_ALLOC_FAIL, "device tail buffers");
-        ctx->tail_C_cap = C;
-    }
-    const size_t tail_bytes = sizeof(float) * C * kHalfOvl;
-    // chunk i reads its initial tail from d_tail[(i+1)&1] and leaves its final tail in d_tail[i&1]
-    const bool use_halo = !tail_in && halo_coef;
-    if (tail_in) NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_tail[1], tail_in, tail_bytes, cudaMemcpyHostToDevice, ctx->slot_stream[0]));
-    else NQ_CUDA(ctx, cudaMemsetAsync(ctx->d_tail[1], 0, tail_bytes, ctx->slot_stream[0]));
-    if (use_halo) NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_halo, halo_coef, row * sizeof(float), cudaMemcpyHostToDevice, ctx->slot_stream[0]));
-
-    long long nchunks = (nframes + chunk - 1) / chunk;
-    for (long long i = 0; i < nchunks; i++) {
-        const int s = (int)(i % S);
-        cudaStream_t st = ctx->slot_stream[s];
-        const long long f0 = i * chunk, n = (f0 + chunk <= nframes) ? chunk : nframes - f0;
-        NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_in[s], coef + f0 * row, n * row * sizeof(float), cudaMemcpyHostToDevice, st));
-        NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags[s], transient + f0, (size_t)n, cudaMemcpyHostToDevice, st));
-        if (i > 0) NQ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->kernel_done[(i - 1) % S], 0));
-        const bool first_with_halo = (i == 0 && use_halo);
-        int rc = enqueue_synth(ctx, plain_layout(C), ctx->d_in[s], ctx->d_flags[s],
-                               first_with_halo ? nullptr : ctx->d_tail[(i + 1) & 1],
-                               first_with_halo ? ctx->d_halo : nullptr, halo_transient ? 1u : 0u, ctx->d_out[s],
-                               ctx->d_tail[i & 1], n, st);
-        if (rc != NQ_OK) return rc;
-        NQ_CUDA(ctx, cudaEventRecord(ctx->kernel_done[s], st));
-        NQ_CUDA(ctx, cudaMemcpyAsync(pcm_out + f0 * row, ctx->d_out[s], n * row * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (i == nchunks - 1 && tail_out)
-            NQ_CUDA(ctx, cudaMemcpyAsync(tail_out, ctx->d_tail[i & 1], tail_bytes, cudaMemcpyDeviceToHost, st));
-    }
-    for (int s = 0; s < S; s++) NQ_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-    return NQ_OK;
+    HostState st;
+    st.tail_in = tail_in;
+    st.tail_out = tail_out;
+    return host_range(ctx, plain_layout(C), coef, transient, nullptr, st, halo_coef, halo_transient ? 1u : 0u, pcm_out, nframes);
 }
 
 }  // namespace
@@ -510,6 +665,100 @@ int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t 
     }
     if (!coef || !transient || !pcm_out) return fail(ctx, NQ_BAD_ARG, "null coef/transient/pcm_out");
     return synth_host_range(ctx, coef, transient, tail_in, nullptr, 0, pcm_out, tail_out, nframes, C);
+}
+
+// ---- post stage + whole phase 2 ------------------------------------------------------------
+int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *frames, const float *hist_in,
+                              const float *mem_in, float *hist_out, float *mem_out, int64_t nframes, int channels,
+                              int streams, int coupled_streams, const unsigned char *mapping, void *stream)
+{
+    if (!ctx) return NQ_BAD_ARG;
+    Layout L;
+    if (mapping) {
+        int rc = check_layout(ctx, channels, streams, coupled_streams, mapping, &L);
+        if (rc != NQ_OK) return rc;
+    } else {
+        if (channels < 1 || channels > 2) return fail(ctx, NQ_BAD_ARG, "without a mapping: one CELT decoder, channels 1 or 2 (got %d)", channels);
+        L = plain_layout(channels);
+    }
+    if (nframes < 0 || nframes > 0x7fffffff) return fail(ctx, NQ_BAD_ARG, "nframes=%lld", (long long)nframes);
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t hist_bytes = sizeof(float) * L.D * kPostHist, mem_bytes = sizeof(float) * L.D;
+    if (nframes == 0) {
+        if (hist_out) {
+            if (hist_in) NQ_CUDA(ctx, cudaMemcpyAsync(hist_out, hist_in, hist_bytes, cudaMemcpyDeviceToDevice, st));
+            else NQ_CUDA(ctx, cudaMemsetAsync(hist_out, 0, hist_bytes, st));
+        }
+        if (mem_out) {
+            if (mem_in) NQ_CUDA(ctx, cudaMemcpyAsync(mem_out, mem_in, mem_bytes, cudaMemcpyDeviceToDevice, st));
+            else NQ_CUDA(ctx, cudaMemsetAsync(mem_out, 0, mem_bytes, st));
+        }
+        return NQ_OK;
+    }
+    if (!pcm || !frames) return fail(ctx, NQ_BAD_ARG, "null pcm/frames");
+    if (reinterpret_cast<uintptr_t>(pcm) & 15) return fail(ctx, NQ_BAD_ARG, "pcm must be a 16-byte aligned device pointer");
+    for (int64_t i = 0; i < nframes * L.streams; i++) {
+        const nq_celt_post_frame &f = frames[i];
+        const int N0 = frames[(i / L.streams) * L.streams].N;
+        const bool okN = f.N == 120 || f.N == 240 || f.N == 480 || f.N == 960;
+        bool ok = okN && f.N == N0;
+        for (int k = 0; k < 3 && ok; k++) {
+            // a zero-gain filter is never evaluated, whatever its period (celt_decoder_clean.c passes pitch 0 then)
+            if (f.gain[k] != 0.f && (f.pitch[k] < 15 || f.pitch[k] > 1022)) ok = false;   // COMBFILTER_MINPERIOD .. 1022
+            if (f.tapset[k] < 0 || f.tapset[k] > 2) ok = false;
+        }
+        if (!ok) return fail(ctx, NQ_BAD_ARG, "frame %lld stream %lld: bad side info (N=%d)", (long long)(i / L.streams), (long long)(i % L.streams), f.N);
+    }
+    int rc = grow(ctx, &ctx->d_pframes_dev, &ctx->pframes_dev_cap, (size_t)nframes * L.streams * sizeof(PostFrame), "post side info");
+    if (rc != NQ_OK) return rc;
+    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pframes_dev, frames, (size_t)nframes * L.streams * sizeof(PostFrame), cudaMemcpyHostToDevice, st));
+    std::vector<PostJob> jobs;
+    build_post_jobs(L, 0, 0, (int)nframes, false, &jobs);
+    if (jobs.empty()) return NQ_OK;
+    if ((int)jobs.size() > ctx->pjobs_dev_cap) {
+        cudaFree(ctx->d_pjobs_dev);
+        ctx->d_pjobs_dev = nullptr;
+        ctx->pjobs_dev_cap = 0;
+        if (cudaMalloc(&ctx->d_pjobs_dev, jobs.size() * sizeof(PostJob)) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "post jobs");
+        ctx->pjobs_dev_cap = (int)jobs.size();
+    }
+    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pjobs_dev, jobs.data(), jobs.size() * sizeof(PostJob), cudaMemcpyHostToDevice, st));
+    return enqueue_post(ctx, L, pcm, ctx->d_pframes_dev, ctx->d_pjobs_dev, (int)jobs.size(), hist_in, mem_in, hist_out, mem_out, st);
+}
+
+int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const nq_celt_post_frame *frames,
+                              const float *tail_in, const float *hist_in, const float *mem_in, float *pcm_out,
+                              float *tail_out, float *hist_out, float *mem_out, int64_t nframes, int channels, int streams,
+                              int coupled_streams, const unsigned char *mapping)
+{
+    if (!ctx) return NQ_BAD_ARG;
+    Layout L;
+    if (mapping) {
+        int rc = check_layout(ctx, channels, streams, coupled_streams, mapping, &L);
+        if (rc != NQ_OK) return rc;
+        if (L.streams > kMaxGroupStreams) return fail(ctx, NQ_UNIMPLEMENTED, "at most %d streams per batch", kMaxGroupStreams);
+    } else {
+        if (channels < 1 || channels > 2) return fail(ctx, NQ_BAD_ARG, "without a mapping: one CELT decoder, channels 1 or 2 (got %d)", channels);
+        L = plain_layout(channels);
+    }
+    if (nframes < 0) return fail(ctx, NQ_BAD_ARG, "nframes=%lld", (long long)nframes);
+    const size_t tail_n = (size_t)L.D * kHalfOvl, hist_n = (size_t)L.D * kPostHist;
+    if (nframes == 0) {
+        if (tail_out) { if (tail_in) memcpy(tail_out, tail_in, 4 * tail_n); else memset(tail_out, 0, 4 * tail_n); }
+        if (hist_out) { if (hist_in) memcpy(hist_out, hist_in, 4 * hist_n); else memset(hist_out, 0, 4 * hist_n); }
+        if (mem_out) { if (mem_in) memcpy(mem_out, mem_in, 4 * (size_t)L.D); else memset(mem_out, 0, 4 * (size_t)L.D); }
+        return NQ_OK;
+    }
+    if (!coef || !transient || !frames || !pcm_out) return fail(ctx, NQ_BAD_ARG, "null coef/transient/frames/pcm_out");
+    for (int64_t i = 0; i < nframes * L.streams; i++)
+        if (frames[i].N != kFrame) return fail(ctx, NQ_UNIMPLEMENTED, "frame %lld: only 20 ms frames (N=960) in a batch, got N=%d",
+                                               (long long)(i / L.streams), frames[i].N);
+    HostState st;
+    st.tail_in = tail_in; st.tail_out = tail_out;
+    st.hist_in = hist_in; st.hist_out = hist_out;
+    st.mem_in = mem_in; st.mem_out = mem_out;
+    return host_range(ctx, L, coef, transient, frames, st, nullptr, 0, pcm_out, nframes);
 }
 
 int nq_celt_synth_batch_host_multi(const int *devices, int ndev, const float *coef, const uint8_t *transient,

@@ -84,6 +84,46 @@ struct MdctCall {
     int ifft_only;     // 1: `in`/`out` are N4 interleaved complex values; only opus_ifft (kiss_fft.c:696) is run
 };
 
+// ---- post stage (celt_post_kernels.cu): comb filter + de-emphasis ----------------------------
+constexpr int kPostHist = 1026;   // COMBFILTER_MAXPERIOD + 2 filtered samples of history per channel (celt.h:187)
+
+// Side information of one frame of one stream: the arguments of the two comb_filter calls at
+// celt_decoder_clean.c:660-669.  Same layout as nq_celt_post_frame (include/nq_celt_synth.h).
+struct PostFrame {
+    int32_t N;           // samples per channel of this frame, 120 << LM
+    int32_t pitch[3];    // postfilter_period_old, postfilter_period, postfilter_pitch (new)
+    float gain[3];
+    int32_t tapset[3];
+};
+
+// One warp's work: `nframes` consecutive frames of 1 or 2 adjacent output channels.
+struct PostJob {
+    long long sample0;   // first sample (per channel) of frame0 inside the pcm buffer
+    int frame0, nframes;
+    int ch0, nch;        // output channel(s) ch0 .. ch0+nch-1
+    int stream_col;      // column of the stream inside a frame's side-info record
+    int state_row;       // row of channel ch0 in the state arrays (decoded-channel order)
+    int reset;           // 1: start from a reset decoder (zero history and memory), ignore *_in
+    int pad_;
+};
+
+struct PostParams {
+    float *pcm;              // [nsamples][C]: celt_sig in, PCM out (in place)
+    const PostFrame *frames; // [nframes][frame_stride]
+    const PostJob *jobs;
+    const float *window;     // window120
+    const float *hist_in;    // [rows][kPostHist] or nullptr
+    const float *mem_in;     // [rows] or nullptr
+    float *hist_out;
+    float *mem_out;
+    int C;
+    int frame_stride;        // streams
+};
+
+size_t post_kernel_smem_bytes();
+cudaError_t prepare_post_kernel();
+cudaError_t launch_post(const PostParams &p, int njobs, cudaStream_t stream);
+
 size_t fast_kernel_smem_bytes();
 int synth_mode(int D, int C, int nstreams, bool identity_map);
 int groups_per_cta(int nstreams);

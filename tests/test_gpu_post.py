@@ -1,0 +1,214 @@
+"""GPU parity tests (-m gpu) of the post stage: comb_filter x2 +
+deemphasis through the C ABI (nq_celt_post_batch_device, nq_celt_decode_batch_host) against the
+oracle's bit-exact restatement and the reference decoder's own PCM.
+
+Bar: |pcm_gpu - pcm_ref| <= 1e-5 (PCM full scale is 1.0, i.e. 1e-5 of full scale) and SNR >= 100 dB.
+The GPU evaluates the de-emphasis IIR as lane segments + a warp scan and contracts a*b+c into
+FMAs, so parity is tolerance-based, not bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_npz, snr_db
+import libnyquist_b200 as nq
+from oracle import port, ref
+
+pytestmark = pytest.mark.gpu
+
+PCM_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def synth():
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    with nq.CeltSynth(0) as s:
+        yield s
+
+
+def assert_pcm(want, got, what):
+    assert want.shape == got.shape, (what, want.shape, got.shape)
+    assert np.isfinite(got).all(), what
+    err = float(np.abs(got.astype(np.float64) - want).max()) if want.size else 0.0
+    assert err <= PCM_TOL, f"{what}: max abs err {err:.3e}"
+    if want.size and np.abs(want).max() > 0:
+        assert snr_db(want, got) >= 100.0, f"{what}: SNR {snr_db(want, got):.1f} dB"
+    return err
+
+
+def rand_frames(rng, nframes, N=960, p_off=0.2):
+    fr = np.zeros(nframes, nq.POST_FRAME_DTYPE)
+    fr["N"] = N
+    pitch = rng.integers(15, 1023, nframes + 2)
+    pitch[rng.uniform(size=nframes + 2) < 0.2] = 15                       # shortest period: 13-sample steps
+    gain = rng.choice([0.09375 * k for k in range(1, 9)], nframes + 2).astype(np.float32)
+    gain[rng.uniform(size=nframes + 2) < p_off] = 0
+    tap = rng.integers(0, 3, nframes + 2)
+    for i in range(nframes):   # hand-over of celt_decoder_clean.c:672-683 (LM != 0: old <- cur <- new)
+        fr["pitch"][i] = pitch[i + 1], pitch[i + 1], pitch[i + 2]
+        fr["gain"][i] = gain[i + 1], gain[i + 1], gain[i + 2]
+        fr["tapset"][i] = tap[i + 1], tap[i + 1], tap[i + 2]
+    fr["pitch"][0][0], fr["gain"][0][0], fr["tapset"][0][0] = pitch[0], gain[0], tap[0]
+    return fr
+
+
+def test_post_fixture_short_opus_tail(synth):
+    """Last 26 frames of short.opus: active post-filter, tapset changes, a transient, the final
+    LM=0 frame; expected values are the reference decoder's PCM."""
+    import torch
+    z = load_npz("post_cases.npz")
+    pcm = torch.from_numpy(z["short_tail.sig"]).cuda()
+    hist, mem = synth.post_batch_torch(pcm, z["short_tail.frames"], torch.from_numpy(z["short_tail.hist_in"]).cuda(),
+                                       torch.from_numpy(z["short_tail.mem_in"]).cuda())
+    torch.cuda.synchronize()
+    assert_pcm(z["short_tail.pcm"], pcm.cpu().numpy(), "short.opus tail")
+    _, want_hist, want_mem = port.post_batch(z["short_tail.sig"], z["short_tail.frames"], z["short_tail.hist_in"],
+                                             z["short_tail.mem_in"])
+    assert np.abs(hist.cpu().numpy() - want_hist).max() <= 1e-5 * 32768
+    assert np.abs(mem.cpu().numpy() - want_mem).max() <= 1e-5 * 32768
+
+
+@pytest.mark.parametrize("C", [1, 2])
+@pytest.mark.parametrize("N", [120, 240, 480, 960])
+def test_post_random_side_info_vs_oracle(synth, C, N):
+    import torch
+    rng = np.random.default_rng(10 * N + C)
+    nframes = 60
+    fr = rand_frames(rng, nframes, N)
+    sig = (rng.standard_normal((nframes * N, C)) * 1500).astype(np.float32)
+    hist_in = (rng.standard_normal((C, nq.POST_HISTORY)) * 1500).astype(np.float32)
+    mem_in = (rng.standard_normal(C) * 500).astype(np.float32)
+    want, want_hist, want_mem = port.post_batch(sig, fr, hist_in, mem_in)
+    pcm = torch.from_numpy(sig).cuda()
+    hist, mem = synth.post_batch_torch(pcm, fr, torch.from_numpy(hist_in).cuda(), torch.from_numpy(mem_in).cuda())
+    torch.cuda.synchronize()
+    assert_pcm(want, pcm.cpu().numpy(), f"C {C} N {N}")
+    assert np.abs(hist.cpu().numpy() - want_hist).max() <= 1e-5 * 32768
+    assert np.abs(mem.cpu().numpy() - want_mem).max() <= 1e-5 * 32768
+    # chaining two calls through the state is invisible (bit for bit)
+    k = 23
+    a = torch.from_numpy(sig[:k * N]).cuda()
+    b = torch.from_numpy(sig[k * N:]).cuda()
+    h1, m1 = synth.post_batch_torch(a, fr[:k], torch.from_numpy(hist_in).cuda(), torch.from_numpy(mem_in).cuda())
+    h2, m2 = synth.post_batch_torch(b, fr[k:], h1, m1)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([a, b]), pcm) and torch.equal(h2, hist) and torch.equal(m2, mem)
+
+
+def test_post_reset_state_and_zero_gain_is_pure_deemphasis(synth):
+    import torch
+    rng = np.random.default_rng(3)
+    fr = np.zeros(5, nq.POST_FRAME_DTYPE)
+    fr["N"] = 960   # gains 0, pitch 0 as celt_decoder_clean.c leaves them for an inactive post-filter
+    sig = (rng.standard_normal((5 * 960, 2)) * 1000).astype(np.float32)
+    pcm = torch.from_numpy(sig).cuda()
+    synth.post_batch_torch(pcm, fr)
+    torch.cuda.synchronize()
+    x = sig.astype(np.float64)
+    y = np.zeros_like(x)
+    m = np.zeros(2)
+    for i in range(len(x)):
+        t = x[i] + m
+        m = 0.85000610 * t
+        y[i] = t / 32768
+    assert_pcm(y.astype(np.float32), pcm.cpu().numpy(), "pure de-emphasis")
+
+
+def test_post_multistream_mapping(synth):
+    """7.1 layout: the post stage runs on the OUTPUT layout, every output channel with the side
+    info of the stream that feeds it; a silent channel stays exactly zero."""
+    import torch
+    rng = np.random.default_rng(8)
+    streams, coupled, mapping = 5, 3, [0, 6, 1, 2, 3, 4, 255, 7]
+    D, nframes = streams + coupled, 40
+    fr = np.stack([rand_frames(rng, nframes) for _ in range(streams)], axis=1)
+    dec = (rng.standard_normal((nframes * 960, D)) * 1200).astype(np.float32)
+    want = np.zeros((nframes * 960, len(mapping)), np.float32)
+    for c, d in enumerate(mapping):
+        if d == 255:
+            continue
+        s = d // 2 if d < 2 * coupled else d - coupled
+        want[:, c:c + 1] = port.post_batch(np.ascontiguousarray(dec[:, d:d + 1]), np.ascontiguousarray(fr[:, s]))[0]
+    sig = np.zeros_like(want)
+    for c, d in enumerate(mapping):
+        if d != 255:
+            sig[:, c] = dec[:, d]
+    pcm = torch.from_numpy(sig).cuda()
+    synth.post_batch_torch(pcm, fr, streams=streams, coupled_streams=coupled, mapping=mapping)
+    torch.cuda.synchronize()
+    got = pcm.cpu().numpy()
+    assert_pcm(want, got, "7.1")
+    assert not got[:, 6].any()
+
+
+def test_post_rejects_bad_side_info(synth):
+    import torch
+    pcm = torch.zeros((960, 2), device="cuda")
+    fr = np.zeros(1, nq.POST_FRAME_DTYPE)
+    fr["N"] = 960
+    fr["gain"][0] = 0.5, 0.5, 0.5
+    fr["pitch"][0] = 14, 100, 100          # below COMBFILTER_MINPERIOD with a live gain
+    with pytest.raises(nq.NqError):
+        synth.post_batch_torch(pcm, fr)
+    fr["pitch"][0] = 100, 100, 100
+    fr["tapset"][0] = 0, 3, 0
+    with pytest.raises(nq.NqError):
+        synth.post_batch_torch(pcm, fr)
+    fr["tapset"][0] = 0, 0, 0
+    fr["N"] = 961
+    with pytest.raises(nq.NqError):
+        synth.post_batch_torch(torch.zeros((961, 2), device="cuda"), fr)
+
+
+# ---- BASELINE configs 1-3 end to end: decoded PCM of every bundled file ----------------------
+CHECKSUMS = {"sb-reverie.opus": (403, 21472602), "sb-reverie-60ms-frames.opus": (719, 21472602), "short.opus": (22, 421930)}
+
+
+@pytest.mark.parametrize("fname", sorted(CHECKSUMS))
+def test_whole_file_pcm_vs_reference_decoder(synth, fname):
+    """Phase 1 = the reference's own entropy decoder (oracle/_ref, compiled in place) recording
+    freq[] and the post-filter parameters; phase 2 = GPU synthesis + post stage over the whole
+    file.  The result must match the reference decoder's PCM (north_star: within 1e-5) and pass
+    the reference's own acceptance test, examples/src/Main.cpp:131-149 (int(sum), length)."""
+    import torch
+    path = os.path.join(os.path.dirname(ref.LIB_PATH), "test_data", fname)
+    if not (ref.available() and os.path.exists(path)):
+        pytest.skip("oracle/_ref (compiled reference + staged test_data) not present")
+    pcm_ref, recs = ref.decode_file(path, record=True)
+    pre_skip, gain = ref.header_info()
+    assert gain == 0
+    frames = port.post_frames_from_records(recs)
+    n20 = len(recs)
+    while n20 and recs[n20 - 1]["coef"].shape[1] != 960:
+        n20 -= 1
+    assert all(r["coef"].shape[1] == 960 and r["nch"] == 2 for r in recs[:n20])
+    coef = np.stack([r["coef"] for r in recs[:n20]])
+    tr = np.array([r["B"] == 8 for r in recs[:n20]], np.uint8)
+    if n20 == len(recs):
+        got, _ = synth.decode_batch(coef, tr, frames)          # ONE call: coefficients in, PCM out
+    else:
+        # short.opus ends with one 2.5 ms (LM=0) frame: batched synthesis for the 20 ms frames, the
+        # single-frame entry for the last one, then the post stage over the whole stream
+        sig, tail = synth.synth_batch(coef, tr)
+        parts = [sig]
+        for r in recs[n20:]:
+            N = r["coef"].shape[1]
+            LM = {120: 0, 240: 1, 480: 2}[N]
+            outs = [np.concatenate([tail[c], np.zeros(N, np.float32)]) for c in range(2)]
+            synth.compute_inv_mdcts(r["B"] if r["B"] > 1 else 0, np.ascontiguousarray(r["coef"]), outs, 2, LM)
+            parts.append(np.stack([o[:N] for o in outs], axis=1))
+            tail = np.stack([o[N:N + 60] for o in outs])
+        d = torch.from_numpy(np.concatenate(parts)).cuda()
+        synth.post_batch_torch(d, frames)
+        torch.cuda.synchronize()
+        got = d.cpu().numpy()
+    got = got[pre_skip:pre_skip + len(pcm_ref)]     # opusfile: pre-skip and end trim (opusfile.c:2673-2721)
+    err = assert_pcm(pcm_ref, got, fname)
+    # the reference's acceptance test: de-interleave, float sum in order
+    total = np.float32(0)
+    flat = np.concatenate([got[:, 0], got[:, 1]])
+    s = float(np.cumsum(flat, dtype=np.float32)[-1])
+    print(f"{fname}: max |err| {err:.2e}, sum {s:.4f}, len {flat.size}")
+    assert (int(s), flat.size) == CHECKSUMS[fname]
