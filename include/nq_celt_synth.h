@@ -122,14 +122,23 @@ NQ_API int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const u
  *              channel mapping[c]; 255 = silent channel; a decoded channel may
  *              feed several outputs or none
  *   pcm_out    [nframes*960][channels]
+ *   frame_offset [nframes] (device) or NULL: first output sample of every
+ *              frame; needed when the batch holds frames shorter than 20 ms
+ *              (SURVEY.md 8(f) row 4).  A flag byte then carries the frame
+ *              size too: bit 0 = transient, bits 1-2 = 3 - LM (0 = 20 ms, so
+ *              plain 0/1 flags keep meaning 20 ms frames).  Such a frame has
+ *              N = 120 << LM coefficients at the start of each 960-float row
+ *              (transient: 1 << LM short blocks interleaved, as the reference).
+ *              NULL: every frame is a 20 ms frame, frame f starts at 960 f.
+ * mapping == NULL: one CELT decoder (streams = 1, channels 1 or 2).
  * At most 14 streams per batch (NQ_UNIMPLEMENTED beyond: one warp per stream,
  * 14 warps per SM).  All pointers except mapping / halo_transient are device
  * pointers; enqueued on `stream`, no synchronisation. */
 NQ_API int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient,
                                          const float *tail_in, const float *halo_coef,
                                          const uint8_t *halo_transient, float *pcm_out, float *tail_out,
-                                         int64_t nframes, int channels, int streams, int coupled_streams,
-                                         const unsigned char *mapping, void *stream);
+                                         const int64_t *frame_offset, int64_t nframes, int channels, int streams,
+                                         int coupled_streams, const unsigned char *mapping, void *stream);
 
 /* ---- post stage: pitch post-filter + de-emphasis ---
  * What celt_decode_with_ec does to out_syn after compute_inv_mdcts: comb_filter

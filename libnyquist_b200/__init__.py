@@ -80,8 +80,8 @@ def load_library():
     L.nq_celt_host_free.argtypes = [vp]
     L.nq_celt_synth_batch_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int64, C.c_int, vp]
     L.nq_celt_synth_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int]
-    L.nq_celt_synth_batch_device_ms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int,
-                                                vp, vp]
+    L.nq_celt_synth_batch_device_ms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int,
+                                                C.c_int, vp, vp]
     L.nq_celt_post_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]
     L.nq_celt_decode_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int,
                                             C.c_int, vp]
@@ -265,7 +265,7 @@ class CeltSynth:
 
     def synth_batch_ms_torch(self, coef, transient, streams: int, coupled_streams: int, mapping,
                              tail_in=None, halo_coef=None, halo_transient=None, out=None, want_tail=True,
-                             stream=None):
+                             stream=None, frame_offset=None):
         """Opus multistream batch (opus_multistream_decoder.c:110, :237-299): coef cuda f32
         [nframes][streams+coupled][960], transient cuda u8 [nframes][streams], mapping: sequence of
         `channels` decoded-channel indices (255 = silent).  Returns (pcm [nframes*960][channels], tail)."""
@@ -275,9 +275,13 @@ class CeltSynth:
         assert transient.is_cuda and transient.dtype == torch.uint8 and transient.is_contiguous()
         nframes = coef.shape[0]
         assert coef.shape == (nframes, D, FRAME) and transient.shape == (nframes, streams)
-        mp = np.ascontiguousarray(mapping, np.uint8)
-        ch = mp.size
-        pcm = out if out is not None else torch.empty((nframes * FRAME, ch), dtype=torch.float32, device=coef.device)
+        mp = None if mapping is None else np.ascontiguousarray(mapping, np.uint8)
+        ch = D if mp is None else mp.size
+        nsamples = nframes * FRAME
+        if frame_offset is not None:   # cuda int64 [nframes + 1]: frames shorter than 20 ms in the batch
+            assert frame_offset.is_cuda and frame_offset.dtype == torch.int64 and frame_offset.shape == (nframes + 1,)
+            nsamples = int(frame_offset[-1])
+        pcm = out if out is not None else torch.empty((nsamples, ch), dtype=torch.float32, device=coef.device)
         tail = torch.empty((D, HALF_OVERLAP), dtype=torch.float32, device=coef.device) if want_tail else None
         st = (stream if stream is not None else torch.cuda.current_stream(coef.device)).cuda_stream
         if st == 0:
@@ -287,8 +291,9 @@ class CeltSynth:
             self._h, C.c_void_p(coef.data_ptr()), C.c_void_p(transient.data_ptr()),
             C.c_void_p(0 if tail_in is None else tail_in.data_ptr()),
             C.c_void_p(0 if halo_coef is None else halo_coef.data_ptr()), _vp(ht), C.c_void_p(pcm.data_ptr()),
-            C.c_void_p(0 if tail is None else tail.data_ptr()), nframes, ch, int(streams), int(coupled_streams),
-            _vp(mp), C.c_void_p(st)))
+            C.c_void_p(0 if tail is None else tail.data_ptr()),
+            C.c_void_p(0 if frame_offset is None else frame_offset.data_ptr()), nframes, ch, int(streams),
+            int(coupled_streams), _vp(mp), C.c_void_p(st)))
         return pcm, tail
 
 

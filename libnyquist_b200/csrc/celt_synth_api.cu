@@ -177,10 +177,13 @@ Layout plain_layout(int C)
     return L;
 }
 
+// halo_flags: bit s = transient flag of stream s of the halo frame (bit 0 for everybody without
+// per-stream flags), bits 30-31 = 3 - LM of the halo frame.
 int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8_t *transient, const float *tail_in,
-                  const float *halo_coef, unsigned halo_transient_bits, float *pcm, float *tail_out, long long nframes,
-                  cudaStream_t stream)
+                  const float *halo_coef, unsigned halo_flags, float *pcm, float *tail_out, long long nframes,
+                  cudaStream_t stream, const long long *frame_offset = nullptr)
 {
+    const unsigned halo_transient_bits = halo_flags & 0x3fffffffu;
     SynthParams p;
     memset(&p, 0, sizeof p);
     p.coef = coef;
@@ -191,6 +194,9 @@ int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const ui
     p.pcm = pcm;
     p.tail_out = tail_out;
     p.tables = ctx->d_fast;
+    p.gen = ctx->d_gen;
+    p.frame_offset = frame_offset;
+    p.halo_lm_shift = (int)(halo_flags >> 30);
     p.nframes = nframes;
     p.D = L.D;
     p.C = L.C;
@@ -401,19 +407,26 @@ int nq_celt_synth_batch_device(nq_celt_ctx *ctx, const float *coef, const uint8_
         (halo_coef && (reinterpret_cast<uintptr_t>(halo_coef) & 15)))
         return fail(ctx, NQ_BAD_ARG, "coef, halo_coef and pcm_out must be 16-byte aligned device pointers");
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    return enqueue_synth(ctx, plain_layout(C), coef, transient, tail_in, halo_coef, halo_transient ? 1u : 0u, pcm_out,
-                         tail_out, nframes, stream ? (cudaStream_t)stream : ctx->stream);
+    const unsigned hf = (unsigned)halo_transient;   // a flag byte: bit 0 transient, bits 1-2 = 3 - LM
+    return enqueue_synth(ctx, plain_layout(C), coef, transient, tail_in, halo_coef, (hf & 1u) | ((hf >> 1 & 3u) << 30),
+                         pcm_out, tail_out, nframes, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
 int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const float *tail_in,
                                   const float *halo_coef, const uint8_t *halo_transient, float *pcm_out,
-                                  float *tail_out, int64_t nframes, int channels, int streams, int coupled_streams,
-                                  const unsigned char *mapping, void *stream)
+                                  float *tail_out, const int64_t *frame_offset, int64_t nframes, int channels,
+                                  int streams, int coupled_streams, const unsigned char *mapping, void *stream)
 {
     if (!ctx) return NQ_BAD_ARG;
     Layout L;
-    int rc = check_layout(ctx, channels, streams, coupled_streams, mapping, &L);
-    if (rc != NQ_OK) return rc;
+    if (mapping) {
+        int rc = check_layout(ctx, channels, streams, coupled_streams, mapping, &L);
+        if (rc != NQ_OK) return rc;
+    } else {
+        if (channels < 1 || channels > 2 || streams != 1)
+            return fail(ctx, NQ_BAD_ARG, "without a mapping: one CELT decoder, channels 1 or 2 (got %d channels, %d streams)", channels, streams);
+        L = plain_layout(channels);
+    }
     if (nframes < 0) return fail(ctx, NQ_BAD_ARG, "nframes=%lld", (long long)nframes);
     if (L.streams > kMaxGroupStreams)
         return fail(ctx, NQ_UNIMPLEMENTED, "at most %d streams per multistream batch (got %d)", kMaxGroupStreams, streams);
@@ -433,9 +446,12 @@ int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, const uin
     unsigned halo_bits = 0;
     if (halo_coef && !tail_in) {
         if (!halo_transient) return fail(ctx, NQ_BAD_ARG, "halo_coef needs halo_transient[streams] (host pointer)");
-        for (int s = 0; s < streams; s++) halo_bits |= (halo_transient[s] ? 1u : 0u) << s;
+        for (int s = 0; s < streams; s++) halo_bits |= (unsigned)(halo_transient[s] & 1) << s;
+        halo_bits |= (unsigned)(halo_transient[0] >> 1 & 3) << 30;
     }
-    return enqueue_synth(ctx, L, coef, transient, tail_in, halo_coef, halo_bits, pcm_out, tail_out, nframes, st);
+    static_assert(sizeof(long long) == sizeof(int64_t), "frame_offset element type");
+    return enqueue_synth(ctx, L, coef, transient, tail_in, halo_coef, halo_bits, pcm_out, tail_out, nframes, st,
+                         reinterpret_cast<const long long *>(frame_offset));
 }
 
 }  // extern "C"
@@ -644,7 +660,8 @@ int synth_host_range(nq_celt_ctx *ctx, const float *coef, const uint8_t *transie
     HostState st;
     st.tail_in = tail_in;
     st.tail_out = tail_out;
-    return host_range(ctx, plain_layout(C), coef, transient, nullptr, st, halo_coef, halo_transient ? 1u : 0u, pcm_out, nframes);
+    const unsigned hf = (unsigned)halo_transient;
+    return host_range(ctx, plain_layout(C), coef, transient, nullptr, st, halo_coef, (hf & 1u) | ((hf >> 1 & 3u) << 30), pcm_out, nframes);
 }
 
 }  // namespace

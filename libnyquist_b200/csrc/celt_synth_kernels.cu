@@ -124,12 +124,12 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 
 // Interleaved output frame [960][C] from the group's planes: output channel c is decoded
 // channel mapping[c] (a gather, opus_multistream_decoder.c:260-299) or silence.
-__device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *frame_out)
+__device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *frame_out, int niter)
 {
     float4 *dst = reinterpret_cast<float4 *>(frame_out) + g.q0;
     uint32_t a0 = g.src[0], a1 = g.src[1], a2 = g.src[2], a3 = g.src[3];
 #pragma unroll 5
-    for (int i = 0; i < g.niter; i++) {
+    for (int i = 0; i < niter; i++) {
         float4 v;
         v.x = lds_f32(a0);
         v.y = lds_f32(a1);
@@ -150,7 +150,7 @@ __device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *fram
 // ------------------------------------------------------------ long frame ---
 // One stereo (or mono: nch == 1) long block per call.  See file header.
 template <int kMode>
-__device__ __forceinline__ void long_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long f,
+__device__ __forceinline__ void long_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off,
                                            int cb, int nch, bool store, bool more, long long fnext,
                                            const float (&w4)[4], GroupCtx &grp)
 {
@@ -242,7 +242,7 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
     }
     if (store && active) {
         if (kStereo) {
-            float4 *dst = reinterpret_cast<float4 *>(p.pcm + f * (kFrame * 2));
+            float4 *dst = reinterpret_cast<float4 *>(p.pcm + off * 2);
             __stcs(dst + 29 - k1, make_float4(H0[0], H0[1], H1[0], H1[1]));
 #pragma unroll
             for (int k2 = 0; k2 < 15; k2++)
@@ -261,7 +261,7 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
             }
         } else {
             // generic channel count: channel pair (cb, cb+1) of an interleaved [n][C] frame
-            float *dst = p.pcm + f * kFrame * p.C + cb;
+            float *dst = p.pcm + off * p.C + cb;
             const int C = p.C;
             if (nch == 2 && (C & 1) == 0) {          // 8-byte aligned {ch, ch+1} pairs
                 __stcs(reinterpret_cast<float2 *>(dst + (58 - 2 * k1) * C), make_float2(H0[0], H0[1]));
@@ -300,7 +300,7 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
 // 8 short blocks per channel (N = 240, N2 = 120, N4 = 60), sub-block b uses
 // coefficients X[b + 8j] (celt_decoder_clean.c:292-300).
 template <int kMode>
-__device__ __forceinline__ void short_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long f,
+__device__ __forceinline__ void short_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off,
                                             int cb, int nch, bool store, bool more, long long fnext, GroupCtx &grp)
 {
     constexpr bool kStereo = kMode == kModeStereo;
@@ -374,11 +374,11 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
     if (store && kMode != kModeGroup) {   // group mode: `stage` IS the stream's plane, stored by the group
         if (kStereo) {
             const float4 *s4 = reinterpret_cast<const float4 *>(stage);
-            float4 *dst = reinterpret_cast<float4 *>(p.pcm + f * (kFrame * 2));
+            float4 *dst = reinterpret_cast<float4 *>(p.pcm + off * 2);
 #pragma unroll
             for (int j = 0; j < 15; j++) __stcs(dst + lane + 32 * j, s4[lane + 32 * j]);
         } else {
-            float *dst = p.pcm + f * kFrame * p.C + cb;
+            float *dst = p.pcm + off * p.C + cb;
             if (nch == 2 && (p.C & 1) == 0) {
                 const float2 *s2 = reinterpret_cast<const float2 *>(stage);
                 for (int n = lane; n < kFrame; n += 32) __stcs(reinterpret_cast<float2 *>(dst + n * p.C), s2[n]);
@@ -393,11 +393,85 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
     __syncwarp();   // staging buffer is reused by the next frame's stage 1
 }
 
+// ------------------------------------------- frames shorter than 20 ms ----
+// LM < 3 (2.5 / 5 / 10 ms frames: N2 = 120 / 240 / 480, or 1 / 2 / 4 short blocks), SURVEY.md
+// section 8(f) row 4.  Rare in practice (the bundled files hold one such frame), so this is a
+// compact, loop-based warp routine that follows the reference formulas literally
+// (mdct.c:295-313, :320-359, :361-377) with the reference's trig table, the N4-point inverse DFT
+// as 30 x R (30-point codelet, then an R-term direct sum) -- the same arithmetic as
+// mdct_backward_generic_kernel below -- and leaves the frame as a [N][2] plane at the start of
+// ws.x.  What matters is that such frames can sit anywhere inside a batch and hand their tail on.
+__device__ __noinline__ void small_frame_planes(const GenericTables *gt, const float *win, float *in_rows, float2 *xbuf,
+                                                float *tails, int lane, int nch, int sh, int is_tr)
+{
+    const int Nf = kFrame >> sh;
+    const int nb = is_tr ? (8 >> sh) : 1;
+    const int N2 = is_tr ? 120 : Nf, N4 = N2 >> 1, R = N4 / 30;
+    const int shift = is_tr ? 3 : sh;
+    const float sine = (float)2 * 3.141592653f * (.125f) / (float)(kMdctN >> shift);   // mdct.c:292
+    float *plane = reinterpret_cast<float *>(xbuf);   // [Nf][2], at most 480 x 2 floats
+    float2 *a_buf = xbuf + 480, *b_buf = a_buf + 240;
+    float *y = reinterpret_cast<float *>(a_buf);      // y[N2] takes a_buf's place once stage 1 has read it
+    const float *trig = gt->trig;
+    for (int ch = 0; ch < nch; ch++) {
+        const float *row = in_rows + ch * kInRowFloats;
+        float *tail = tails + ch * kHalfOvl;
+        for (int b = 0; b < nb; b++) {
+            for (int i = lane; i < N4; i += 32) {
+                const float x1 = row[b + 2 * i * nb], x2 = row[b + (N2 - 1 - 2 * i) * nb];
+                const float t0 = trig[i << shift], t1 = trig[(N4 - i) << shift];
+                const float yr = -(x2 * t0) + x1 * t1, yi = -(x2 * t1) - x1 * t0;
+                a_buf[i] = make_float2(yr - yi * sine, yi + yr * sine);
+            }
+            __syncwarp();
+            if (lane < R) {
+                float2 g[30];
+#pragma unroll
+                for (int n1 = 0; n1 < 30; n1++) g[n1] = a_buf[R * n1 + lane];
+                idft30(g);
+#pragma unroll
+                for (int k1 = 0; k1 < 30; k1++) {
+                    float sn, cs;
+                    sincospif(2.0f * (float)(lane * k1) / (float)N4, &sn, &cs);
+                    b_buf[lane * 30 + k1] = cmulc(g[k1], cs, sn);
+                }
+            }
+            __syncwarp();
+            for (int k = lane; k < N4; k += 32) {
+                const int k1 = k % 30, k2 = k / 30;
+                float2 acc = make_float2(0.f, 0.f);
+                for (int n2 = 0; n2 < R; n2++) {
+                    float sn, cs;
+                    sincospif(2.0f * (float)((n2 * k2) % R) / (float)R, &sn, &cs);
+                    acc = cadd(acc, cmulc(b_buf[n2 * 30 + k1], cs, sn));
+                }
+                const float t0 = trig[k << shift], t1 = trig[(N4 - k) << shift];
+                const float yr = acc.x * t0 - acc.y * t1, yi = acc.y * t0 + acc.x * t1;
+                y[2 * k] = -(yr - yi * sine);
+                y[N2 - 1 - 2 * k] = yi + yr * sine;
+            }
+            __syncwarp();
+            for (int n = lane; n < N2; n += 32) {
+                float o;
+                if (n < kHalfOvl) o = win[kOverlap - 1 - n] * tail[n] - win[n] * y[kHalfOvl - 1 - n];
+                else if (n < kOverlap) o = win[kOverlap - 1 - n] * tail[kOverlap - 1 - n] + win[n] * y[n - kHalfOvl];
+                else o = y[n - kHalfOvl];
+                plane[(b * N2 + n) * 2 + ch] = o;
+            }
+            __syncwarp();
+            for (int i = lane; i < kHalfOvl; i += 32) tail[i] = y[N2 - kHalfOvl + i];
+            __syncwarp();
+        }
+    }
+}
+
 // ----------------------------------------------------------- fast kernel ---
 // kWarps = warps per CTA: 14 (what shared memory allows), or 12 for group shapes that cannot use
 // more than 12 anyway -- three warps per scheduler instead of four lifts the register cap from
 // 128 to 168 per thread, which the group variant needs to stay out of local memory.
-template <int kMode, int kWarps>
+// kAnySize: the batch may hold frames shorter than 20 ms (p.frame_offset != nullptr).  A separate
+// instantiation, so that the common all-20-ms kernel keeps its register allocation.
+template <int kMode, int kWarps, bool kAnySize>
 __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid_constant__ SynthParams p)
 {
     constexpr bool kStereo = kMode == kModeStereo;
@@ -506,21 +580,57 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                 tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
             }
         }
-        int is_tr = f < 0 ? ((p.halo_transient >> halo_bit) & 1) : flags[f * p.flag_stride];
+        // flag byte of a frame: bit 0 = transient (short blocks), bits 1-2 = 3 - LM (0: 20 ms frame)
+        int flag = f < 0 ? (p.halo_lm_shift << 1) | ((p.halo_transient >> halo_bit) & 1) : flags[f * p.flag_stride];
         for (; f < f1; f++) {
             const bool more = f + 1 < f1;
-            const int next_tr = more ? flags[(f + 1) * p.flag_stride] : 0;
+            const int next_flag = more ? flags[(f + 1) * p.flag_stride] : 0;
             while (!mbar_try_wait(&ws.bar, phase)) {}
             phase ^= 1;
             const bool store = f >= f0;
-            if (!is_tr) long_frame<kMode>(p, tb, ws, lane, f, cb, nch, store, more, f + 1, w4, grp);
-            else short_frame<kMode>(p, tb, ws, lane, f, cb, nch, store, more, f + 1, grp);
+            const long long off = (kAnySize && store) ? p.frame_offset[f] : f * kFrame;
+            const int sh = kAnySize ? (flag >> 1) & 3 : 0;
+            int niter = grp.niter;
+            if (sh == 0) {
+                if (!(flag & 1)) long_frame<kMode>(p, tb, ws, lane, off, cb, nch, store, more, f + 1, w4, grp);
+                else short_frame<kMode>(p, tb, ws, lane, off, cb, nch, store, more, f + 1, grp);
+            } else {
+                if (kMode == kModeGroup && grp.pending) {   // see long_frame
+                    group_sync(grp);
+                    grp.pending = false;
+                }
+                small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, nch, sh, flag & 1);
+                if (more && lane == 0) {   // ws.in fully consumed: prefetch the next frame
+                    mbar_expect_tx(&ws.bar, nch * kFrame * 4);
+                    for (int ch = 0; ch < nch; ch++)
+                        tma_load_row(ws.in + ch * kInRowFloats, p.coef + (f + 1) * p.D * kFrame + (cb + ch) * kFrame, kFrame * 4, &ws.bar);
+                }
+                const int Nf = kFrame >> sh;
+                if (kMode == kModeGroup) {
+                    const int tg = grp.q0;
+                    niter = tg < grp.T2 ? ((Nf / 4) * p.C - tg + grp.T2 - 1) / grp.T2 : 0;
+                } else if (store) {
+                    const float *plane = reinterpret_cast<const float *>(ws.x);
+                    if (kStereo) {
+                        const float4 *s4 = reinterpret_cast<const float4 *>(plane);
+                        float4 *dst = reinterpret_cast<float4 *>(p.pcm + off * 2);
+                        for (int i = lane; i < Nf / 2; i += 32) __stcs(dst + i, s4[i]);
+                    } else {
+                        float *dst = p.pcm + off * p.C + cb;
+                        for (int idx = lane; idx < 2 * Nf; idx += 32) {
+                            const int n = idx >> 1, ch = idx & 1;
+                            if (ch < nch) dst[n * p.C + ch] = plane[idx];
+                        }
+                    }
+                    __syncwarp();   // the plane is overwritten by the next frame's stage 1
+                }
+            }
             if (kMode == kModeGroup && store) {
                 group_sync(grp);   // every stream's plane of frame f is complete
-                group_store_frame(grp, p.pcm + f * kFrame * p.C);
+                group_store_frame(grp, p.pcm + off * p.C, niter);
                 grp.pending = true;   // ... and must stay intact until the whole group is through this pass
             }
-            is_tr = next_tr;
+            flag = next_flag;
         }
         __syncwarp();
         if (f1 == p.nframes && p.tail_out != nullptr) {
@@ -560,18 +670,29 @@ int synth_mode(int D, int C, int nstreams, bool identity_map)
     return kModeDirect;
 }
 
+template <int kMode, int kWarps>
+static cudaError_t prepare_variant(int smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(celt_synth_kernel<kMode, kWarps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(celt_synth_kernel<kMode, kWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 cudaError_t prepare_kernels()
 {
     const int smem = (int)fast_kernel_smem_bytes();
-    const void *kernels[] = {(const void *)celt_synth_kernel<kModeStereo, kWarpsPerCta>,
-                             (const void *)celt_synth_kernel<kModeGroup, kWarpsPerCta>,
-                             (const void *)celt_synth_kernel<kModeGroup, 12>,
-                             (const void *)celt_synth_kernel<kModeDirect, kWarpsPerCta>};
-    for (const void *k : kernels) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    cudaError_t e = prepare_variant<kModeStereo, kWarpsPerCta>(smem);
+    if (e == cudaSuccess) e = prepare_variant<kModeGroup, kWarpsPerCta>(smem);
+    if (e == cudaSuccess) e = prepare_variant<kModeGroup, 12>(smem);
+    if (e == cudaSuccess) e = prepare_variant<kModeDirect, kWarpsPerCta>(smem);
+    return e;
+}
+
+template <int kMode, int kWarps>
+static void launch_variant(const SynthParams &p, unsigned grid, size_t smem, cudaStream_t stream)
+{
+    if (p.frame_offset) celt_synth_kernel<kMode, kWarps, true><<<grid, kWarps * 32, smem, stream>>>(p);
+    else celt_synth_kernel<kMode, kWarps, false><<<grid, kWarps * 32, smem, stream>>>(p);
 }
 
 cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream_t stream, int *launched_ctas)
@@ -588,11 +709,11 @@ cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream
     if (ctas < 1) ctas = 1;
     if (launched_ctas) *launched_ctas = (int)ctas;
     const size_t smem = sizeof(FastTables) + (size_t)warps * sizeof(WarpSmem);
-    const unsigned grid = (unsigned)ctas, block = warps * 32;
-    if (mode == kModeStereo) celt_synth_kernel<kModeStereo, kWarpsPerCta><<<grid, block, smem, stream>>>(p);
-    else if (mode == kModeGroup && warps == 12) celt_synth_kernel<kModeGroup, 12><<<grid, block, smem, stream>>>(p);
-    else if (mode == kModeGroup) celt_synth_kernel<kModeGroup, kWarpsPerCta><<<grid, block, smem, stream>>>(p);
-    else celt_synth_kernel<kModeDirect, kWarpsPerCta><<<grid, block, smem, stream>>>(p);
+    const unsigned grid = (unsigned)ctas;
+    if (mode == kModeStereo) launch_variant<kModeStereo, kWarpsPerCta>(p, grid, smem, stream);
+    else if (mode == kModeGroup && warps == 12) launch_variant<kModeGroup, 12>(p, grid, smem, stream);
+    else if (mode == kModeGroup) launch_variant<kModeGroup, kWarpsPerCta>(p, grid, smem, stream);
+    else launch_variant<kModeDirect, kWarpsPerCta>(p, grid, smem, stream);
     return cudaGetLastError();
 }
 

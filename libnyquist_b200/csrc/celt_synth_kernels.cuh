@@ -60,6 +60,8 @@ struct SynthParams {
     float *pcm;                 // [nframes*960][C]
     float *tail_out;            // [D][60] or nullptr
     const FastTables *tables;
+    const GenericTables *gen;          // reference trig table: frames shorter than 20 ms
+    const long long *frame_offset;     // [nframes] first sample of every frame, or nullptr: frame f starts at 960 f
     long long nframes;
     long long frames_per_run;
     long long nruns;
@@ -68,6 +70,7 @@ struct SynthParams {
     int npairs;                 // kModeDirect: channel pairs per frame
     int nstreams;               // kModeGroup: warps per group
     int store_threads;          // kModeGroup: threads of a group in the store pass (group_store_threads())
+    int halo_lm_shift;          // 3 - LM of the halo frame
     int halo_transient;         // flag(s) of the halo frame: bit s = stream s (bit 0 for everybody if !flag_per_stream)
     int flag_stride;            // bytes between the flag records of consecutive frames
     int flag_per_stream;        // 0: every stream reads column 0; 1: stream / pair s reads column s

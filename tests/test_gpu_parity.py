@@ -226,6 +226,81 @@ def test_multistream_rejects_bad_layouts(synth):
     assert e.value.code == -5
 
 
+# ---- frames shorter than 20 ms anywhere inside a batch ---------------------
+def oracle_any_size(coef, flags, tail_in):
+    """compute_inv_mdcts frame by frame (oracle), any LM: coef [nframes][C][960] (first 120<<LM
+    valid), flags [nframes] (bit 0 transient, bits 1-2 = 3-LM).  Returns (pcm [nsamples][C], tail, offsets)."""
+    nframes, C, _ = coef.shape
+    tail = np.zeros((C, 60), np.float32) if tail_in is None else tail_in.copy()
+    out, offs, pos = [], [], 0
+    for f in range(nframes):
+        LM = 3 - ((int(flags[f]) >> 1) & 3)
+        N = 120 << LM
+        X = np.ascontiguousarray(coef[f, :, :N])
+        bufs = [np.concatenate([tail[c], np.zeros(N, np.float32)]) for c in range(C)]
+        port.compute_inv_mdcts((1 << LM) if flags[f] & 1 else 0, X, bufs, C, LM)
+        out.append(np.stack([b[:N] for b in bufs], axis=1))
+        tail = np.stack([b[N:N + 60] for b in bufs])
+        offs.append(pos)
+        pos += N
+    offs.append(pos)
+    return np.concatenate(out), tail, np.array(offs, np.int64)
+
+
+@pytest.mark.parametrize("C", [1, 2])
+def test_batch_with_short_frames_everywhere(synth, C):
+    import torch
+    rng = np.random.default_rng(40 + C)
+    nframes = 900
+    coef, tr = rand_batch(rng, nframes, C, 0.2)
+    lm = rng.choice([3, 3, 3, 2, 1, 0], nframes)
+    flags = (tr | ((3 - lm) << 1)).astype(np.uint8)
+    for f in range(nframes):
+        coef[f, :, 120 << lm[f]:] = 7777.0     # must be ignored
+    tail_in = (rng.standard_normal((C, 60)) * 100).astype(np.float32)
+    want, want_tail, offs = oracle_any_size(coef, flags, tail_in)
+    d_coef, d_fl, d_off = torch.from_numpy(coef).cuda(), torch.from_numpy(flags).cuda().reshape(-1, 1), torch.from_numpy(offs).cuda()
+    pcm, tail = synth.synth_batch_ms_torch(d_coef, d_fl, 1, C - 1, None, tail_in=torch.from_numpy(tail_in).cuda(),
+                                           frame_offset=d_off)
+    torch.cuda.synchronize()
+    assert_parity(want, pcm.cpu().numpy(), f"any-size C {C}")
+    assert_parity(want_tail, tail.cpu().numpy(), "tail")
+    # shard start on a halo frame that is itself a short frame
+    cut = int(np.nonzero(lm[1:] < 3)[0][5]) + 2
+    assert lm[cut - 1] < 3
+    part, _ = synth.synth_batch_ms_torch(d_coef[cut:].contiguous(), d_fl[cut:].contiguous(), 1, C - 1, None,
+                                         halo_coef=d_coef[cut - 1].contiguous(), halo_transient=flags[cut - 1:cut],
+                                         frame_offset=(d_off[cut:] - d_off[cut]).contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(part, pcm[int(offs[cut]):])
+
+
+def test_multistream_batch_with_short_frames(synth):
+    import torch
+    streams, coupled, mapping = MS_LAYOUTS["surround_7.1"]
+    D = streams + coupled
+    rng = np.random.default_rng(77)
+    nframes = 300
+    coef, _ = rand_batch(rng, nframes, D, 0.0)
+    lm = rng.choice([3, 3, 2, 1, 0], nframes)
+    tr = (rng.uniform(size=(nframes, streams)) < 0.2).astype(np.uint8)
+    flags = (tr | ((3 - lm[:, None]) << 1)).astype(np.uint8)
+    dec = []
+    for s in range(streams):
+        rows = [2 * s, 2 * s + 1] if s < coupled else [s + coupled]
+        w, _, offs = oracle_any_size(np.ascontiguousarray(coef[:, rows]), flags[:, s], None)
+        dec.append((rows, w))
+    want = np.zeros((int(offs[-1]), len(mapping)), np.float32)
+    for c, d in enumerate(mapping):
+        for rows, w in dec:
+            if d in rows:
+                want[:, c] = w[:, rows.index(d)]
+    pcm, _ = synth.synth_batch_ms_torch(torch.from_numpy(coef).cuda(), torch.from_numpy(flags).cuda(), streams, coupled,
+                                        mapping, frame_offset=torch.from_numpy(offs).cuda())
+    torch.cuda.synchronize()
+    assert_parity(want, pcm.cpu().numpy(), "7.1 any-size")
+
+
 def test_edge_cases_and_error_codes(synth):
     rng = np.random.default_rng(5)
     # empty batch: tail passes through
