@@ -173,7 +173,9 @@ NQ_API int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt
  * (synthesis, channel mapping, post-filter, de-emphasis), chunks pipelined
  * H2D / kernels / D2H.  Decoder state (tail [D][60], hist [D][1026], mem [D];
  * NULL in = reset decoder, NULL out = discard) lets a stream be fed in pieces.
- * 20 ms frames only (NQ_UNIMPLEMENTED otherwise). */
+ * Frames shorter than 20 ms are allowed anywhere: frames[].N = 120 << LM and
+ * the flag bytes (see frame_offset above) must agree (NQ_BAD_ARG otherwise);
+ * pcm_out then holds sum(N) samples per channel. */
 NQ_API int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient,
                                      const nq_celt_post_frame *frames, const float *tail_in, const float *hist_in,
                                      const float *mem_in, float *pcm_out, float *tail_out, float *hist_out,

@@ -338,7 +338,7 @@ class CeltSynth:
         assert tr.shape[1] == (streams if mp is not None else 1)
         fr = np.ascontiguousarray(frames, POST_FRAME_DTYPE).reshape(nframes, streams)
         ti, hi, mi = (None, None, None) if state is None else [np.ascontiguousarray(a, np.float32) for a in state]
-        pcm = np.empty((nframes * FRAME, ch), np.float32)
+        pcm = np.empty((int(fr["N"][:, 0].sum()), ch), np.float32)
         to = np.zeros((D, HALF_OVERLAP), np.float32)
         ho = np.zeros((D, POST_HISTORY), np.float32)
         mo = np.zeros((D,), np.float32)

@@ -99,6 +99,8 @@ struct nq_celt_ctx {
     size_t pframes_cap[kSlots] = {};
     PostJob *d_pjobs[kSlots] = {};
     int pjobs_cap[kSlots] = {};
+    long long *d_offs[kSlots] = {};
+    size_t offs_cap[kSlots] = {};
     float *d_hist[2] = {};
     float *d_mem[2] = {};
     int post_rows_cap = 0;
@@ -375,7 +377,7 @@ void nq_celt_ctx_destroy(nq_celt_ctx *ctx)
     cudaFree(ctx->d_tail[0]);
     cudaFree(ctx->d_tail[1]);
     cudaFree(ctx->d_halo);
-    for (int s = 0; s < nq_celt_ctx::kSlots; s++) { cudaFree(ctx->d_pframes[s]); cudaFree(ctx->d_pjobs[s]); }
+    for (int s = 0; s < nq_celt_ctx::kSlots; s++) { cudaFree(ctx->d_pframes[s]); cudaFree(ctx->d_pjobs[s]); cudaFree(ctx->d_offs[s]); }
     for (int i = 0; i < 2; i++) { cudaFree(ctx->d_hist[i]); cudaFree(ctx->d_mem[i]); }
     cudaFree(ctx->d_pframes_dev);
     cudaFree(ctx->d_pjobs_dev);
@@ -605,6 +607,17 @@ int host_range(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8
         else NQ_CUDA(ctx, cudaMemsetAsync(ctx->d_mem[1], 0, mem_bytes, s0));
     }
 
+    // frames shorter than 20 ms: output offsets come from the side info (prefix sums of N)
+    std::vector<long long> offs, rel;
+    if (pframes) {
+        bool any = false;
+        for (long long f = 0; f < nframes && !any; f++) any = pframes[f * L.streams].N != kFrame;
+        if (any) {
+            offs.resize(nframes + 1);
+            offs[0] = 0;
+            for (long long f = 0; f < nframes; f++) offs[f + 1] = offs[f] + pframes[f * L.streams].N;
+        }
+    }
     std::vector<PostJob> jobs;
     const long long nchunks = (nframes + chunk - 1) / chunk;
     for (long long i = 0; i < nchunks; i++) {
@@ -623,8 +636,23 @@ int host_range(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8
         }
         if (i > 0) NQ_CUDA(ctx, cudaStreamWaitEvent(sst, ctx->kernel_done[(i - 1) % S], 0));
         const bool first_with_halo = (i == 0 && use_halo);
+        const long long *d_off = nullptr;
+        long long out_first = f0 * kFrame, out_count = n * kFrame;   // samples per channel
+        if (!offs.empty()) {
+            rel.resize(n);
+            for (long long k = 0; k < n; k++) rel[k] = offs[f0 + k] - offs[f0];
+            size_t cap = ctx->offs_cap[s];
+            int rc0 = grow(ctx, &ctx->d_offs[s], &cap, (size_t)n * sizeof(long long), "frame offsets");
+            ctx->offs_cap[s] = cap;
+            if (rc0 != NQ_OK) return rc0;
+            NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_offs[s], rel.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, sst));
+            d_off = ctx->d_offs[s];
+            out_first = offs[f0];
+            out_count = offs[f0 + n] - offs[f0];
+        }
         int rc = enqueue_synth(ctx, L, ctx->d_in[s], ctx->d_flags[s], first_with_halo ? nullptr : ctx->d_tail[(i + 1) & 1],
-                               first_with_halo ? ctx->d_halo : nullptr, halo_bits, ctx->d_out[s], ctx->d_tail[i & 1], n, sst);
+                               first_with_halo ? ctx->d_halo : nullptr, halo_bits, ctx->d_out[s], ctx->d_tail[i & 1], n, sst,
+                               d_off);
         if (rc != NQ_OK) return rc;
         if (pframes) {
             jobs.clear();
@@ -642,7 +670,8 @@ int host_range(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8
             if (rc != NQ_OK) return rc;
         }
         NQ_CUDA(ctx, cudaEventRecord(ctx->kernel_done[s], sst));
-        NQ_CUDA(ctx, cudaMemcpyAsync(pcm_out + f0 * out_row, ctx->d_out[s], n * out_row * sizeof(float), cudaMemcpyDeviceToHost, sst));
+        NQ_CUDA(ctx, cudaMemcpyAsync(pcm_out + out_first * L.C, ctx->d_out[s], (size_t)out_count * L.C * sizeof(float),
+                                     cudaMemcpyDeviceToHost, sst));
         if (i == nchunks - 1) {
             if (st.tail_out) NQ_CUDA(ctx, cudaMemcpyAsync(st.tail_out, ctx->d_tail[i & 1], tail_bytes, cudaMemcpyDeviceToHost, sst));
             if (pframes && st.hist_out) NQ_CUDA(ctx, cudaMemcpyAsync(st.hist_out, ctx->d_hist[i & 1], hist_bytes, cudaMemcpyDeviceToHost, sst));
@@ -768,9 +797,14 @@ int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t
         return NQ_OK;
     }
     if (!coef || !transient || !frames || !pcm_out) return fail(ctx, NQ_BAD_ARG, "null coef/transient/frames/pcm_out");
-    for (int64_t i = 0; i < nframes * L.streams; i++)
-        if (frames[i].N != kFrame) return fail(ctx, NQ_UNIMPLEMENTED, "frame %lld: only 20 ms frames (N=960) in a batch, got N=%d",
-                                               (long long)(i / L.streams), frames[i].N);
+    const int fcols = L.per_stream_flags ? L.streams : 1;
+    for (int64_t f = 0; f < nframes; f++)
+        for (int sidx = 0; sidx < L.streams; sidx++) {
+            const int N = frames[f * L.streams + sidx].N, flag = transient[f * fcols + (L.per_stream_flags ? sidx : 0)];
+            if (N != (kFrame >> ((flag >> 1) & 3)) || (flag >> 3))
+                return fail(ctx, NQ_BAD_ARG, "frame %lld stream %d: flag byte 0x%02x does not say N=%d (bit 0 transient, bits 1-2 = 3-LM)",
+                            (long long)f, sidx, flag, N);
+        }
     HostState st;
     st.tail_in = tail_in; st.tail_out = tail_out;
     st.hist_in = hist_in; st.hist_out = hist_out;

@@ -180,30 +180,16 @@ def test_whole_file_pcm_vs_reference_decoder(synth, fname):
     pre_skip, gain = ref.header_info()
     assert gain == 0
     frames = port.post_frames_from_records(recs)
-    n20 = len(recs)
-    while n20 and recs[n20 - 1]["coef"].shape[1] != 960:
-        n20 -= 1
-    assert all(r["coef"].shape[1] == 960 and r["nch"] == 2 for r in recs[:n20])
-    coef = np.stack([r["coef"] for r in recs[:n20]])
-    tr = np.array([r["B"] == 8 for r in recs[:n20]], np.uint8)
-    if n20 == len(recs):
-        got, _ = synth.decode_batch(coef, tr, frames)          # ONE call: coefficients in, PCM out
-    else:
-        # short.opus ends with one 2.5 ms (LM=0) frame: batched synthesis for the 20 ms frames, the
-        # single-frame entry for the last one, then the post stage over the whole stream
-        sig, tail = synth.synth_batch(coef, tr)
-        parts = [sig]
-        for r in recs[n20:]:
-            N = r["coef"].shape[1]
-            LM = {120: 0, 240: 1, 480: 2}[N]
-            outs = [np.concatenate([tail[c], np.zeros(N, np.float32)]) for c in range(2)]
-            synth.compute_inv_mdcts(r["B"] if r["B"] > 1 else 0, np.ascontiguousarray(r["coef"]), outs, 2, LM)
-            parts.append(np.stack([o[:N] for o in outs], axis=1))
-            tail = np.stack([o[N:N + 60] for o in outs])
-        d = torch.from_numpy(np.concatenate(parts)).cuda()
-        synth.post_batch_torch(d, frames)
-        torch.cuda.synchronize()
-        got = d.cpu().numpy()
+    assert all(r["nch"] == 2 for r in recs)
+    # short.opus ends with one 2.5 ms (LM=0) frame: rows are padded to 960, the flag byte says LM
+    coef = np.zeros((len(recs), 2, 960), np.float32)
+    flags = np.zeros(len(recs), np.uint8)
+    for i, r in enumerate(recs):
+        N = r["coef"].shape[1]
+        coef[i, :, :N] = r["coef"]
+        LM = {120: 0, 240: 1, 480: 2, 960: 3}[N]
+        flags[i] = (1 if r["B"] > 1 else 0) | ((3 - LM) << 1)
+    got, _ = synth.decode_batch(coef, flags, frames)          # ONE call: coefficients in, PCM out
     got = got[pre_skip:pre_skip + len(pcm_ref)]     # opusfile: pre-skip and end trim (opusfile.c:2673-2721)
     err = assert_pcm(pcm_ref, got, fname)
     # the reference's acceptance test: de-interleave, float sum in order
