@@ -182,6 +182,41 @@ NQ_API int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const 
                                      float *mem_out, int64_t nframes, int channels, int streams,
                                      int coupled_streams, const unsigned char *mapping);
 
+/* ---- frame sink: phase 1 -> phase 2 hand-over ------
+ * The restructured celt_decode_with_ec stops after denormalise_bands
+ * (celt_decoder_clean.c:620-636) and, instead of compute_inv_mdcts / comb_filter
+ * / deemphasis (:656-723), pushes the frame here; INTEGRATION.md shows the
+ * reference-side patch.  One sink per Ogg Opus link / multistream decoder
+ * (arguments of opus_multistream_decoder_create, opus_multistream_decoder.c:110).
+ * The sink keeps pushed frames in pinned host memory and the phase-2 decoder
+ * state (IMDCT tail, comb-filter history, de-emphasis memory) across flushes. */
+typedef struct nq_celt_sink nq_celt_sink;
+NQ_API int nq_celt_sink_create(nq_celt_sink **out, int channels, int streams, int coupled_streams,
+                               const unsigned char *mapping);
+NQ_API void nq_celt_sink_destroy(nq_celt_sink *sink);
+NQ_API const char *nq_celt_sink_last_error(const nq_celt_sink *sink);
+/* One decoded CELT frame of stream `stream` (opus_multistream order), in decode
+ * order: freq [CC][N] as it stands at celt_decoder_clean.c:636 (CC = 2 for a
+ * coupled stream, 1 for a mono one), N = 120 << LM, shortBlocks = 0 or 1 << LM
+ * (:273-284), post = the comb_filter arguments of the frame (:660-669). */
+NQ_API int nq_celt_sink_push(nq_celt_sink *sink, int stream, const float *freq, int CC, int N, int shortBlocks,
+                             const nq_celt_post_frame *post);
+NQ_API int64_t nq_celt_sink_pending_frames(const nq_celt_sink *sink);
+NQ_API int64_t nq_celt_sink_pending_samples(const nq_celt_sink *sink);   /* per channel */
+/* Phase 2 for everything pushed since the last flush (every stream must have
+ * pushed the same number of frames): pcm_out [*nsamples][channels] host buffer,
+ * float PCM in [-1, 1] in output-channel order. */
+NQ_API int nq_celt_sink_flush(nq_celt_sink *sink, nq_celt_ctx *ctx, float *pcm_out, int64_t capacity_samples,
+                              int64_t *nsamples);
+/* Same, into a pinned buffer the sink owns (valid until the next flush or
+ * nq_celt_sink_destroy): saves the caller a page-locked allocation per file. */
+NQ_API int nq_celt_sink_flush_pinned(nq_celt_sink *sink, nq_celt_ctx *ctx, const float **pcm, int64_t *nsamples);
+/* Pinned blocks of destroyed sinks are recycled process-wide (page-locking is
+ * slow); this releases them. */
+NQ_API void nq_celt_sink_trim_pool(void);
+/* OPUS_RESET_STATE (celt_decoder_clean.c:846-859): forget tail, history, memory. */
+NQ_API void nq_celt_sink_reset(nq_celt_sink *sink);
+
 /* Same as _host, frames sharded contiguously over `ndev` devices (devices[i]
  * = CUDA ordinal; NULL => 0..ndev-1) with one host thread + context per
  * device and NO device-to-device traffic: a shard that starts mid-stream

@@ -41,6 +41,9 @@ EXPORTED_SYMBOLS = [
     "nq_celt_device_count", "nq_celt_launch_count", "nq_celt_host_alloc", "nq_celt_host_free",
     "nq_celt_synth_batch_device", "nq_celt_synth_batch_device_ms", "nq_celt_synth_batch_host",
     "nq_celt_synth_batch_host_multi", "nq_celt_post_batch_device", "nq_celt_decode_batch_host",
+    "nq_celt_sink_create", "nq_celt_sink_destroy", "nq_celt_sink_last_error", "nq_celt_sink_push",
+    "nq_celt_sink_pending_frames", "nq_celt_sink_pending_samples", "nq_celt_sink_flush", "nq_celt_sink_reset",
+    "nq_celt_sink_flush_pinned", "nq_celt_sink_trim_pool",
     "nq_clt_mdct_backward", "nq_clt_mdct_backward_B1_C2", "nq_celt_mdct_backward_host",
     "nq_compute_inv_mdcts", "nq_opus_ifft_host", "processMDCTCuda", "processMDCTCudaB1C2", "cleanupCudaBuffers",
     "printCudaVersion", "nq_celt_debug_tables",
@@ -85,6 +88,17 @@ def load_library():
     L.nq_celt_post_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]
     L.nq_celt_decode_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int,
                                             C.c_int, vp]
+    L.nq_celt_sink_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp]
+    L.nq_celt_sink_destroy.argtypes = [vp]
+    L.nq_celt_sink_last_error.argtypes = [vp]
+    L.nq_celt_sink_last_error.restype = C.c_char_p
+    L.nq_celt_sink_push.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.nq_celt_sink_pending_frames.argtypes = [vp]
+    L.nq_celt_sink_pending_frames.restype = C.c_int64
+    L.nq_celt_sink_pending_samples.argtypes = [vp]
+    L.nq_celt_sink_pending_samples.restype = C.c_int64
+    L.nq_celt_sink_flush.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.nq_celt_sink_reset.argtypes = [vp]
     L.nq_celt_synth_batch_host_multi.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int]
     L.nq_clt_mdct_backward.argtypes = [vp, fp, fp, fp, C.c_int, C.c_int, C.c_int]
     L.nq_clt_mdct_backward.restype = None
@@ -346,6 +360,54 @@ class CeltSynth:
                                                       _vp(pcm), _vp(to), _vp(ho), _vp(mo), nframes, ch, int(streams),
                                                       int(coupled_streams), _vp(mp)))
         return pcm, (to, ho, mo)
+
+
+class FrameSink:
+    """nq_celt_sink: what the restructured celt_decode_with_ec pushes frames into (phase 1) and
+    the one call that turns them into PCM (phase 2)."""
+
+    def __init__(self, channels: int, streams: int, coupled_streams: int, mapping):
+        self._L = load_library()
+        mp = np.ascontiguousarray(mapping, np.uint8)
+        assert mp.size == channels
+        h = C.c_void_p()
+        rc = self._L.nq_celt_sink_create(C.byref(h), channels, streams, coupled_streams, _vp(mp))
+        if rc != NQ_OK:
+            raise NqError(rc, "nq_celt_sink_create: bad layout")
+        self._h, self.channels = h, channels
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.nq_celt_sink_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != NQ_OK:
+            raise NqError(rc, self._L.nq_celt_sink_last_error(self._h).decode())
+
+    def push(self, stream: int, freq: np.ndarray, shortBlocks: int, post) -> None:
+        """freq [CC][N] float32; post: one POST_FRAME_DTYPE record."""
+        _f32c(freq, "freq")
+        CC, N = freq.shape
+        pf = np.ascontiguousarray(post, POST_FRAME_DTYPE).reshape(1)
+        self._check(self._L.nq_celt_sink_push(self._h, int(stream), _vp(freq), CC, N, int(shortBlocks), _vp(pf)))
+
+    @property
+    def pending_frames(self) -> int:
+        return int(self._L.nq_celt_sink_pending_frames(self._h))
+
+    def flush(self, synth: "CeltSynth") -> np.ndarray:
+        n = int(self._L.nq_celt_sink_pending_samples(self._h))
+        pcm = np.empty((n, self.channels), np.float32)
+        got = C.c_int64(0)
+        self._check(self._L.nq_celt_sink_flush(self._h, synth._h, _vp(pcm), n, C.byref(got)))
+        assert got.value == n
+        return pcm
+
+    def reset(self) -> None:
+        self._L.nq_celt_sink_reset(self._h)
 
 
 def synth_batch_multi_gpu(coef: np.ndarray, transient: np.ndarray, tail_in=None, devices=None):

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libnq_celt_b200.so")
 
-SOURCES = ["celt_synth_kernels.cu", "celt_post_kernels.cu", "celt_synth_api.cu"]
+SOURCES = ["celt_synth_kernels.cu", "celt_post_kernels.cu", "celt_synth_api.cu", "celt_frame_sink.cu"]
 HEADERS = ["celt_synth_kernels.cuh", "celt_fft_codelets.cuh", "celt_consts.cuh",
            os.path.join("..", "..", "include", "nq_celt_synth.h")]
 

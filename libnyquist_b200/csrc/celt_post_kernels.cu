@@ -172,13 +172,40 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
     int base = 0;   // ring index of the current frame's sample 0 (history sits just below it)
     long long s0 = job.sample0;
     const PostFrame *fr = p.frames + (size_t)job.frame0 * p.frame_stride + job.stream_col;
+    // Plain stereo, 20 ms frames (the common case): the NEXT frame's 7680 bytes are fetched into
+    // registers before the current frame is filtered, so the HBM latency hides behind the
+    // recurrences instead of adding to every frame.
+    constexpr bool kCanPrefetch = NCH == 2;
+    const bool stereo2 = NCH == 2 && C == 2;
+    float4 nxt[15];
+    bool have_nxt = false;
+    if (kCanPrefetch && stereo2 && job.nframes > 0 && fr->N == kFrame) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(p.pcm + s0 * 2);
+#pragma unroll
+        for (int k = 0; k < 15; k++) nxt[k] = __ldcs(g4 + lane + 32 * k);
+        have_nxt = true;
+    }
+    PostFrame pf_next;
+    if (job.nframes > 0) pf_next = *fr;
     for (int f = 0; f < job.nframes; f++, fr += p.frame_stride) {
-        const PostFrame pf = *fr;
+        const PostFrame pf = pf_next;
+        if (f + 1 < job.nframes) pf_next = fr[p.frame_stride];   // side info one frame ahead, like the samples
         const int N = pf.N;
         float *g = p.pcm + s0 * C + job.ch0;
         // frame -> ring (raw synthesis output)
-        if (NCH == 2 && C == 2) {
+        if (kCanPrefetch && have_nxt) {
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                const int i = lane + 32 * k;
+                sm.ring[0][(base + 2 * i) & kRingMask] = nxt[k].x;
+                sm.ring[1][(base + 2 * i) & kRingMask] = nxt[k].y;
+                sm.ring[0][(base + 2 * i + 1) & kRingMask] = nxt[k].z;
+                sm.ring[1][(base + 2 * i + 1) & kRingMask] = nxt[k].w;
+            }
+            have_nxt = false;
+        } else if (NCH == 2 && C == 2) {
             const float4 *g4 = reinterpret_cast<const float4 *>(g);
+#pragma unroll 5
             for (int i = lane; i < N / 2; i += 32) {
                 const float4 v = __ldcs(g4 + i);
                 sm.ring[0][(base + 2 * i) & kRingMask] = v.x;
@@ -187,15 +214,23 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
                 sm.ring[1][(base + 2 * i + 1) & kRingMask] = v.w;
             }
         } else if (NCH == 2 && ((C | job.ch0) & 1) == 0) {   // 8-byte aligned {ch0, ch0+1} pairs
+#pragma unroll 6
             for (int i = lane; i < N; i += 32) {
                 const float2 v = __ldcs(reinterpret_cast<const float2 *>(g + (size_t)i * C));
                 sm.ring[0][(base + i) & kRingMask] = v.x;
                 sm.ring[1][(base + i) & kRingMask] = v.y;
             }
         } else {
+#pragma unroll 6
             for (int i = lane; i < N; i += 32)
 #pragma unroll
                 for (int ch = 0; ch < NCH; ch++) sm.ring[ch][(base + i) & kRingMask] = __ldcs(g + (size_t)i * C + ch);
+        }
+        if (kCanPrefetch && stereo2 && f + 1 < job.nframes && pf_next.N == kFrame) {
+            const float4 *g4 = reinterpret_cast<const float4 *>(p.pcm + (s0 + N) * 2);
+#pragma unroll
+            for (int k = 0; k < 15; k++) nxt[k] = __ldcs(g4 + lane + 32 * k);
+            have_nxt = true;
         }
         __syncwarp();
         // celt_decoder_clean.c:660-669: [0,120) fades old -> cur; [120,240) fades cur -> new; [240,N) new

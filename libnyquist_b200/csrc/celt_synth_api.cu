@@ -241,11 +241,12 @@ int check_layout(nq_celt_ctx *ctx, int channels, int streams, int coupled, const
     L->coupled = coupled;
     L->D = streams + coupled;
     L->per_stream_flags = true;
-    L->identity = false;
+    L->identity = channels == L->D;
     for (int c = 0; c < channels; c++) {
         if (mapping[c] != 255 && mapping[c] >= L->D)
             return fail(ctx, NQ_BAD_ARG, "mapping[%d]=%d names no decoded channel (streams+coupled=%d)", c, mapping[c], L->D);
         L->mapping[c] = mapping[c];
+        if (mapping[c] != c) L->identity = false;
     }
     return NQ_OK;
 }

@@ -1,0 +1,79 @@
+"""GPU tests (-m gpu) of the two-phase decoder end to end:
+integration/_build/libnyquist_twophase.so is the REFERENCE's own library (bundled Ogg/Opus +
+Common.cpp, compiled in place by integration/Makefile) with the CELT synthesis overlaid away and
+integration/OpusDecoderTwoPhase.cpp in place of src/OpusDecoder.cpp.  nqr::NyquistIO::Load on it
+must return the AudioData the unmodified reference returns.
+
+Bar: |pcm - reference pcm| <= 1e-5 (north_star), identical length / channel count, and the
+reference's own acceptance test (examples/src/Main.cpp:131-149: int(sum), length).
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, snr_db
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+LIB = os.path.join(ROOT, "integration", "_build", "libnyquist_twophase.so")
+CHECKSUMS = {"sb-reverie.opus": (403, 21472602), "sb-reverie-60ms-frames.opus": (719, 21472602), "short.opus": (22, 421930)}
+
+
+@pytest.fixture(scope="module")
+def twophase():
+    if not os.path.exists(LIB):
+        pytest.skip("integration/_build/libnyquist_twophase.so not built (needs /root/reference; make -C integration)")
+    L = C.CDLL(LIB)
+    L.nq_twophase_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t),
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.nq_twophase_free.argtypes = [C.POINTER(C.c_float)]
+    return L
+
+
+def load(L, path):
+    p = C.POINTER(C.c_float)()
+    n, ch, sr = C.c_size_t(0), C.c_int(0), C.c_int(0)
+    tm = (C.c_double * 3)()
+    t0 = time.perf_counter()
+    rc = L.nq_twophase_load(path.encode(), C.byref(p), C.byref(n), C.byref(ch), C.byref(sr), tm)
+    wall = time.perf_counter() - t0
+    if rc != 0:
+        return None, 0, 0, None, wall
+    a = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+    L.nq_twophase_free(p)
+    return a.reshape(-1, ch.value), ch.value, sr.value, list(tm), wall
+
+
+@pytest.mark.parametrize("fname", sorted(CHECKSUMS))
+def test_nyquistio_load_two_phase_matches_reference(twophase, fname):
+    path = os.path.join(os.path.dirname(ref.LIB_PATH), "test_data", fname)
+    if not (ref.available() and os.path.exists(path)):
+        pytest.skip("oracle/_ref (compiled reference + staged test_data) not present")
+    load(twophase, path)                       # warm-up: CUDA context, pinned pools
+    got, ch, sr, tm, wall = load(twophase, path)
+    t0 = time.perf_counter()
+    want, _ = ref.decode_file(path)
+    t_ref = time.perf_counter() - t0
+    assert got is not None and (ch, sr) == (2, 48000)
+    assert got.shape == want.shape
+    err = float(np.abs(got.astype(np.float64) - want).max())
+    assert err <= 1e-5 and snr_db(want, got) >= 100.0, err
+    flat = np.concatenate([got[:, c] for c in range(ch)])
+    s = float(np.cumsum(flat, dtype=np.float32)[-1])
+    assert (int(s), flat.size) == CHECKSUMS[fname]
+    print(f"\n{fname}: Load {wall * 1e3:.0f} ms (phase 1 CPU {tm[0] * 1e3:.0f} ms, phase 2 GPU {tm[1] * 1e3:.0f} ms, "
+          f"trim {tm[2] * 1e3:.0f} ms) vs reference decode (decoded twice: count + fill) {t_ref * 1e3:.0f} ms; "
+          f"max |err| {err:.2e}, sum {s:.4f}")
+
+
+def test_two_phase_load_errors_like_the_reference(twophase, tmp_path):
+    bad = tmp_path / "noise.opus"
+    bad.write_bytes(np.random.default_rng(0).integers(0, 256, 5000, dtype=np.uint8).tobytes())
+    got, *_ = load(twophase, str(bad))          # not an Ogg Opus file: Load throws, as the reference's does
+    assert got is None
+    got, *_ = load(twophase, str(tmp_path / "missing.opus"))
+    assert got is None
