@@ -211,6 +211,16 @@ NQ_API int nq_celt_sink_flush(nq_celt_sink *sink, nq_celt_ctx *ctx, float *pcm_o
 /* Same, into a pinned buffer the sink owns (valid until the next flush or
  * nq_celt_sink_destroy): saves the caller a page-locked allocation per file. */
 NQ_API int nq_celt_sink_flush_pinned(nq_celt_sink *sink, nq_celt_ctx *ctx, const float **pcm, int64_t *nsamples);
+/* Streaming phase 2: after attach, every complete block of 2048 frames is
+ * decoded on a worker thread while the caller keeps pushing (phase 1 and phase 2
+ * overlap), and decoded sample p of every channel is written to
+ * dst[(p - skip_samples) * channels + c] when 0 <= p - skip_samples < dst_samples
+ * -- the positional pre-skip / end-trim window opusfile applies
+ * (opusfile.c:2673-2721).  finish() decodes the last partial block, waits for
+ * the worker and reports how many samples per channel were decoded in all. */
+NQ_API int nq_celt_sink_attach(nq_celt_sink *sink, nq_celt_ctx *ctx, float *dst, int64_t skip_samples,
+                               int64_t dst_samples);
+NQ_API int nq_celt_sink_finish(nq_celt_sink *sink, int64_t *decoded_samples);
 /* Pinned blocks of destroyed sinks are recycled process-wide (page-locking is
  * slow); this releases them. */
 NQ_API void nq_celt_sink_trim_pool(void);

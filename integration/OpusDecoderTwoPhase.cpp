@@ -9,8 +9,10 @@
 //            off by integration/overlay: the range decoder / PVQ / denormalisation run unchanged on
 //            the CPU and every frame's coefficients + side info land in an nq_celt_sink (pinned
 //            host memory).  The PCM opusfile hands back is a placeholder; only its COUNT is used.
-//   phase 2  ONE nq_celt_sink_flush: batched inverse MDCT + overlap-add + multistream channel
-//            routing + post-filter + de-emphasis on the B200, float PCM straight back.
+//   phase 2  batched inverse MDCT + overlap-add + multistream channel routing + post-filter +
+//            de-emphasis on the B200, one call per block of 2048 frames on the sink's worker thread
+//            WHILE phase 1 decodes the next block (nq_celt_sink_attach / _finish), float PCM
+//            straight into AudioData.samples.
 //   then     what the layers above celt_decode_with_ec do to the samples, which is positional:
 //            opusfile drops OpusHead.pre_skip samples at the head and trims the end to the final
 //            granule position (opusfile.c:2673-2721); opus_decode_frame applies the header gain
@@ -107,44 +109,48 @@ private:
         if (nq_celt_sink_create(&sink.s, ch, header->stream_count, header->coupled_count, header->mapping) != NQ_OK)
             throw std::runtime_error("two-phase Opus decoder: unsupported channel layout");
 
-        // ---- phase 1: entropy decode of the whole file, frames -> sink ----
+        // ---- phase 1: entropy decode of the whole file, frames -> sink; phase 2 follows block by
+        // block on the sink's worker thread and writes straight into d->samples through the
+        // positional window opusfile applies: pre_skip samples dropped at the head, the end trimmed
+        // to the final granule position (opusfile.c:2673-2721) ----
+        const int64_t preSkip = header->pre_skip;
+        float *out = d->samples.data();
+        if (nq_celt_sink_attach(sink.s, device_context(), out, preSkip, totalSamples) != NQ_OK)
+            throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(sink.s));
         const double t0 = now_s();
         std::vector<float> placeholder(size_t(5760) * ch);   // 120 ms, the largest Opus packet
         int64_t framesRead = 0;
+        bool readError = false;
         nq_phase1_begin(sink.s);
         for (;;) {
             const int n = op_read_float(fileHandle, placeholder.data(), (int)placeholder.size(), nullptr);
             if (n == 0) break;   // EOF
             if (n < 0) {
-                nq_phase1_end();
                 std::cerr << "Opus decode error: " << n << std::endl;
-                return false;
+                readError = true;
+                break;
             }
             framesRead += n;
         }
         const nq_phase1_stats st = nq_phase1_end();
+        const double t1 = now_s();
+
+        // ---- phase 2, the rest: last partial block + wait for the worker ----
+        int64_t decoded = 0;
+        const int rc = nq_celt_sink_finish(sink.s, &decoded);
+        const double t2 = now_s();
+        if (readError) return false;
         if (st.saw_silk)
             throw std::runtime_error("two-phase Opus decoder: SILK / hybrid packets are not supported (CELT-only streams)");
         if (st.error) throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(sink.s));
         if (st.frames && st.streams_seen != header->stream_count)
             throw std::runtime_error("two-phase Opus decoder: stream count mismatch");
-        const double t1 = now_s();
-
-        // ---- phase 2: one batched GPU call ----
-        const int64_t decoded = nq_celt_sink_pending_samples(sink.s);
-        const int64_t preSkip = header->pre_skip;
+        if (rc != NQ_OK)
+            throw std::runtime_error(std::string("two-phase Opus decoder: phase 2 failed: ") + nq_celt_sink_last_error(sink.s));
         if (framesRead != totalSamples || decoded < preSkip + totalSamples)
             throw std::runtime_error("two-phase Opus decoder: sample accounting does not match opusfile's");
-        const float *full = nullptr;   // pinned, owned by the sink
-        int64_t got = 0;
-        const int rc = nq_celt_sink_flush_pinned(sink.s, device_context(), &full, &got);
-        if (rc != NQ_OK || got != decoded)
-            throw std::runtime_error(std::string("two-phase Opus decoder: phase 2 failed: ") + nq_celt_sink_last_error(sink.s));
-        const double t2 = now_s();
 
         // ---- positional post-processing of the layers above the CELT decoder ----
-        float *out = d->samples.data();
-        memcpy(out, full + size_t(preSkip) * ch, sizeof(float) * size_t(totalSamples) * ch);
         // header gain: opusfile programs OPUS_SET_GAIN with OpusHead.output_gain (Q8 dB, default
         // OP_HEADER_GAIN), opus_decode_frame scales by celt_exp2(6.48814081e-4f * gain)
         int gainQ8 = header->output_gain;

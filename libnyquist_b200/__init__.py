@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     "nq_celt_synth_batch_host_multi", "nq_celt_post_batch_device", "nq_celt_decode_batch_host",
     "nq_celt_sink_create", "nq_celt_sink_destroy", "nq_celt_sink_last_error", "nq_celt_sink_push",
     "nq_celt_sink_pending_frames", "nq_celt_sink_pending_samples", "nq_celt_sink_flush", "nq_celt_sink_reset",
-    "nq_celt_sink_flush_pinned", "nq_celt_sink_trim_pool",
+    "nq_celt_sink_flush_pinned", "nq_celt_sink_trim_pool", "nq_celt_sink_attach", "nq_celt_sink_finish",
     "nq_clt_mdct_backward", "nq_clt_mdct_backward_B1_C2", "nq_celt_mdct_backward_host",
     "nq_compute_inv_mdcts", "nq_opus_ifft_host", "processMDCTCuda", "processMDCTCudaB1C2", "cleanupCudaBuffers",
     "printCudaVersion", "nq_celt_debug_tables",
@@ -99,6 +99,8 @@ def load_library():
     L.nq_celt_sink_pending_samples.restype = C.c_int64
     L.nq_celt_sink_flush.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
     L.nq_celt_sink_reset.argtypes = [vp]
+    L.nq_celt_sink_attach.argtypes = [vp, vp, vp, C.c_int64, C.c_int64]
+    L.nq_celt_sink_finish.argtypes = [vp, C.POINTER(C.c_int64)]
     L.nq_celt_synth_batch_host_multi.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int64, C.c_int]
     L.nq_clt_mdct_backward.argtypes = [vp, fp, fp, fp, C.c_int, C.c_int, C.c_int]
     L.nq_clt_mdct_backward.restype = None
@@ -408,6 +410,19 @@ class FrameSink:
 
     def reset(self) -> None:
         self._L.nq_celt_sink_reset(self._h)
+
+    # streaming phase 2 (worker thread per sink, overlaps with the pushes)
+    def attach(self, synth: "CeltSynth", dst: np.ndarray, skip_samples: int = 0) -> None:
+        """dst: float32 [nsamples][channels], filled in the background as blocks complete."""
+        _f32c(dst, "dst")
+        assert dst.ndim == 2 and dst.shape[1] == self.channels
+        self._dst = dst   # keep alive
+        self._check(self._L.nq_celt_sink_attach(self._h, synth._h, _vp(dst), int(skip_samples), dst.shape[0]))
+
+    def finish(self) -> int:
+        got = C.c_int64(0)
+        self._check(self._L.nq_celt_sink_finish(self._h, C.byref(got)))
+        return got.value
 
 
 def synth_batch_multi_gpu(coef: np.ndarray, transient: np.ndarray, tail_in=None, devices=None):
