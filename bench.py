@@ -178,6 +178,105 @@ def make_device_batch(torch, frames, device, seed):
     return coef, tr
 
 
+def extras(torch, np, nq, synth, dev, peak):
+    """Informational legs outside the contract (N = 1 only, a few seconds): the other channel
+    layouts of BASELINE.json's configs on the same kernel family, the PCIe ceiling the e2e leg runs
+    against, and the end-to-end file decode (nqr::NyquistIO::Load) of the two-phase build next to
+    the unmodified reference's, when both libraries travelled with the repo."""
+    out = {}
+
+    def timed(fn, steps=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    g = torch.Generator(device=dev).manual_seed(7)
+    shapes = {}
+    for name, frames, streams, coupled, mapping, p_tr in (
+            ("mono", 2_000_000, 1, 0, [0], P_TRANSIENT),
+            ("stereo_all_transient", 1_000_000, 1, 1, [0, 1], 1.0),
+            ("surround_5.1_multistream", 400_000, 4, 2, [0, 4, 1, 2, 3, 5], P_TRANSIENT),
+            ("surround_7.1_multistream", 300_000, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7], P_TRANSIENT)):
+        D = streams + coupled
+        c = torch.empty((frames, D, 960), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g)
+        t = (torch.rand((frames, streams), generator=g, device=dev) < p_tr).to(torch.uint8)
+        o = torch.empty((frames * 960, len(mapping)), dtype=torch.float32, device=dev)
+        ms = timed(lambda: synth.synth_batch_ms_torch(c, t, streams, coupled, mapping, out=o, want_tail=False))
+        gbs = frames * 960 * 4 * (D + len(mapping)) / (ms * 1e-3) / 1e9
+        shapes[name] = {"frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3), "GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+        del c, t, o
+    out["other_layouts_device_resident"] = shapes
+
+    # PCIe ceiling of the e2e leg: concurrent pinned H2D + D2H copies of 256 MB each
+    n = 64 << 20
+    h_a = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    h_b = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    d_a = torch.empty(n, dtype=torch.float32, device=dev)
+    d_b = torch.empty(n, dtype=torch.float32, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+
+    for _ in range(2):
+        both()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        both()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 5
+    out["pcie_concurrent_copy_GBps_each_way"] = n * 4 / dt / 1e9
+    del h_a, h_b, d_a, d_b
+
+    # end-to-end file decode, BASELINE.json configs[0]
+    try:
+        import ctypes as C
+        from oracle import ref
+        lib = os.path.join(ROOT, "integration", "_build", "libnyquist_twophase.so")
+        path = os.path.join(ROOT, "oracle", "_ref", "test_data", "sb-reverie.opus")
+        if os.path.exists(lib) and os.path.exists(path) and ref.load_available():
+            L = C.CDLL(lib)
+            L.nq_twophase_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t),
+                                           C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+            L.nq_twophase_free.argtypes = [C.POINTER(C.c_float)]
+            best = None
+            for _ in range(3):
+                p, cnt, ch, sr = C.POINTER(C.c_float)(), C.c_size_t(0), C.c_int(0), C.c_int(0)
+                tm = (C.c_double * 3)()
+                t0 = time.perf_counter()
+                rc = L.nq_twophase_load(path.encode(), C.byref(p), C.byref(cnt), C.byref(ch), C.byref(sr), tm)
+                dt = time.perf_counter() - t0
+                assert rc == 0
+                got = np.ctypeslib.as_array(p, shape=(cnt.value,)).copy()
+                L.nq_twophase_free(p)
+                if best is None or dt < best[0]:
+                    best = (dt, list(tm))
+            ref_best = None
+            for _ in range(2):
+                want, _, dt = ref.nyquist_load(path)
+                ref_best = dt if ref_best is None else min(ref_best, dt)
+            err = float(np.abs(got.reshape(-1, 2) - want).max())
+            out["file_decode_sb_reverie_opus"] = {
+                "what": "nqr::NyquistIO::Load, 223.7 s of stereo audio, 11184 CELT frames (BASELINE.json configs[0])",
+                "two_phase_ms": best[0] * 1e3, "phase1_cpu_entropy_decode_ms": best[1][0] * 1e3,
+                "phase2_gpu_tail_after_phase1_ms": best[1][1] * 1e3, "reference_cpu_ms": ref_best * 1e3,
+                "speedup": ref_best / best[0], "max_abs_pcm_err": err}
+    except Exception as e:   # informational leg: never fail the bench line
+        out["file_decode_error"] = repr(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +286,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational other-shapes / file-decode legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -326,6 +426,10 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         v, cores, kind, sample, _ = cpu_reference_run(65536, 2, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    if not args.no_extras and world == 1:
+        del coef, pcm
+        torch.cuda.empty_cache()
+        line["extras"] = extras(torch, np, nq, synth, dev, peak)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -172,3 +172,35 @@ def deemphasis(x: np.ndarray, mem: np.ndarray) -> np.ndarray:
     assert mem.dtype == np.float32 and mem.shape == (Cn,)
     lib().nqref_deemphasis(rows, _fp(pcm), N, Cn, _fp(mem))
     return pcm
+
+
+# ---- the reference's own end-to-end file decode: nqr::NyquistIO::Load -------------------------
+LOAD_LIB_PATH = os.path.join(HERE, "_ref", "libnyquist_ref.so")
+_load_lib = None
+
+
+def load_available() -> bool:
+    return os.path.exists(LOAD_LIB_PATH)
+
+
+def nyquist_load(path: str):
+    """nqr::NyquistIO::Load of the UNMODIFIED reference (Common.cpp:36, OpusDecoder.cpp:39-183).
+    Returns (samples [n][channels] f32, sample_rate, seconds spent inside Load incl. the copy out)."""
+    import time
+    global _load_lib
+    if _load_lib is None:
+        L = C.CDLL(LOAD_LIB_PATH)
+        L.nqref_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t),
+                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.nqref_free.argtypes = [C.POINTER(C.c_float)]
+        _load_lib = L
+    p = C.POINTER(C.c_float)()
+    n, ch, sr = C.c_size_t(0), C.c_int(0), C.c_int(0)
+    t0 = time.perf_counter()
+    rc = _load_lib.nqref_load(path.encode(), C.byref(p), C.byref(n), C.byref(ch), C.byref(sr))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        raise RuntimeError(f"reference NyquistIO::Load failed for {path}")
+    a = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+    _load_lib.nqref_free(p)
+    return a.reshape(-1, ch.value), sr.value, dt

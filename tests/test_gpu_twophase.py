@@ -55,9 +55,13 @@ def test_nyquistio_load_two_phase_matches_reference(twophase, fname):
         pytest.skip("oracle/_ref (compiled reference + staged test_data) not present")
     load(twophase, path)                       # warm-up: CUDA context, pinned pools
     got, ch, sr, tm, wall = load(twophase, path)
-    t0 = time.perf_counter()
-    want, _ = ref.decode_file(path)
-    t_ref = time.perf_counter() - t0
+    if ref.load_available():     # the unmodified reference's own NyquistIO::Load, same shim, same box
+        ref.nyquist_load(path)
+        want, sr_ref, t_ref = ref.nyquist_load(path)
+        assert sr_ref == sr
+    else:
+        want, _ = ref.decode_file(path)
+        t_ref = float("nan")
     assert got is not None and (ch, sr) == (2, 48000)
     assert got.shape == want.shape
     err = float(np.abs(got.astype(np.float64) - want).max())
@@ -65,8 +69,8 @@ def test_nyquistio_load_two_phase_matches_reference(twophase, fname):
     flat = np.concatenate([got[:, c] for c in range(ch)])
     s = float(np.cumsum(flat, dtype=np.float32)[-1])
     assert (int(s), flat.size) == CHECKSUMS[fname]
-    print(f"\n{fname}: Load {wall * 1e3:.0f} ms (phase 1 CPU {tm[0] * 1e3:.0f} ms, phase 2 GPU {tm[1] * 1e3:.0f} ms, "
-          f"trim {tm[2] * 1e3:.0f} ms) vs reference decode (decoded twice: count + fill) {t_ref * 1e3:.0f} ms; "
+    print(f"\n{fname}: Load {wall * 1e3:.0f} ms (phase 1 CPU {tm[0] * 1e3:.0f} ms, phase 2 tail {tm[1] * 1e3:.0f} ms, "
+          f"gain {tm[2] * 1e3:.0f} ms) vs the reference's own CPU Load {t_ref * 1e3:.0f} ms; "
           f"max |err| {err:.2e}, sum {s:.4f}")
 
 
