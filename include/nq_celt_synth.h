@@ -131,9 +131,10 @@ NQ_API int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const u
  *              (transient: 1 << LM short blocks interleaved, as the reference).
  *              NULL: every frame is a 20 ms frame, frame f starts at 960 f.
  * mapping == NULL: one CELT decoder (streams = 1, channels 1 or 2).
- * At most 14 streams per batch (NQ_UNIMPLEMENTED beyond: one warp per stream,
- * 14 warps per SM).  All pointers except mapping / halo_transient are device
- * pointers; enqueued on `stream`, no synchronisation. */
+ * One warp per coupled stream and one per PAIR of mono streams, at most 14
+ * warps per batch layout (NQ_UNIMPLEMENTED beyond; 7.1 surround needs 4).  All
+ * pointers except mapping / halo_transient are device pointers; enqueued on
+ * `stream`, no synchronisation. */
 NQ_API int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient,
                                          const float *tail_in, const float *halo_coef,
                                          const uint8_t *halo_transient, float *pcm_out, float *tail_out,

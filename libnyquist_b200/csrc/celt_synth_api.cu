@@ -203,26 +203,40 @@ int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const ui
     p.D = L.D;
     p.C = L.C;
     p.npairs = (L.D + 1) / 2;
-    p.nstreams = L.streams;
     p.flag_stride = L.per_stream_flags ? L.streams : 1;
     p.flag_per_stream = L.per_stream_flags ? 1 : 0;
-    const int mode = synth_mode(L.D, L.C, L.streams, L.identity);
+    // warps per group: one per coupled stream, one per PAIR of mono streams (two mono streams with
+    // their own transient flags share a warp like the two channels of a coupled stream)
+    const int nmono = L.streams - L.coupled;
+    const int nslots = L.coupled + (nmono + 1) / 2;
+    p.nstreams = nslots;
+    const int mode = synth_mode(L.D, L.C, nslots, L.identity);
     if (mode == kModeDirect && (!L.identity || L.per_stream_flags))
-        return fail(ctx, NQ_UNIMPLEMENTED, "a channel mapping needs streams <= %d (got %d)", kMaxGroupStreams, L.streams);
+        return fail(ctx, NQ_UNIMPLEMENTED, "a channel mapping needs at most %d coupled streams + pairs of mono streams (got %d)",
+                    kMaxGroupStreams, nslots);
+    if (L.per_stream_flags && L.streams > 30) return fail(ctx, NQ_UNIMPLEMENTED, "at most 30 streams with their own flags");
     long long resident = (long long)ctx->num_sms * kWarpsPerCta / p.npairs;
     if (mode == kModeGroup) {
-        resident = (long long)ctx->num_sms * groups_per_cta(L.streams);
-        p.store_threads = group_store_threads(L.C, L.streams);
-        for (int s = 0; s < L.streams; s++) {
-            p.streams[s].nch = s < L.coupled ? 2 : 1;
-            p.streams[s].row = (uint8_t)(s < L.coupled ? 2 * s : s + L.coupled);
-            p.streams[s].flag_col = (uint8_t)(L.per_stream_flags ? s : 0);
+        resident = (long long)ctx->num_sms * groups_per_cta(nslots);
+        p.store_threads = group_store_threads(L.C, nslots);
+        for (int s = 0; s < L.coupled; s++) {
+            p.streams[s].nch = 2;
+            p.streams[s].row = (uint8_t)(2 * s);
+            p.streams[s].flag_col = p.streams[s].flag_col1 = (uint8_t)(L.per_stream_flags ? s : 0);
+        }
+        for (int j = 0; j < nmono; j += 2) {
+            StreamDesc &sd = p.streams[L.coupled + j / 2];
+            const int s0 = L.coupled + j;
+            sd.nch = j + 1 < nmono ? 2 : 1;
+            sd.row = (uint8_t)(2 * L.coupled + j);
+            sd.flag_col = (uint8_t)(L.per_stream_flags ? s0 : 0);
+            sd.flag_col1 = (uint8_t)(L.per_stream_flags && sd.nch == 2 ? s0 + 1 : sd.flag_col);
         }
         for (int c = 0; c < L.C; c++) {
             const int d = L.mapping[c];
             if (d == 255) p.chan_src[c] = 0xffffu;   // muted channel, opus_multistream_decoder.c:291-299
             else if (d < 2 * L.coupled) p.chan_src[c] = (uint16_t)(((d >> 1) << 1) | (d & 1));
-            else p.chan_src[c] = (uint16_t)((d - L.coupled) << 1);
+            else p.chan_src[c] = (uint16_t)(((L.coupled + (d - 2 * L.coupled) / 2) << 1) | ((d - 2 * L.coupled) & 1));
         }
     }
     plan_runs(nframes, resident, &p.frames_per_run, &p.nruns);
@@ -431,8 +445,6 @@ int nq_celt_synth_batch_device_ms(nq_celt_ctx *ctx, const float *coef, const uin
         L = plain_layout(channels);
     }
     if (nframes < 0) return fail(ctx, NQ_BAD_ARG, "nframes=%lld", (long long)nframes);
-    if (L.streams > kMaxGroupStreams)
-        return fail(ctx, NQ_UNIMPLEMENTED, "at most %d streams per multistream batch (got %d)", kMaxGroupStreams, streams);
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     if (nframes == 0) {
@@ -784,7 +796,6 @@ int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t
     if (mapping) {
         int rc = check_layout(ctx, channels, streams, coupled_streams, mapping, &L);
         if (rc != NQ_OK) return rc;
-        if (L.streams > kMaxGroupStreams) return fail(ctx, NQ_UNIMPLEMENTED, "at most %d streams per batch", kMaxGroupStreams);
     } else {
         if (channels < 1 || channels > 2) return fail(ctx, NQ_BAD_ARG, "without a mapping: one CELT decoder, channels 1 or 2 (got %d)", channels);
         L = plain_layout(channels);

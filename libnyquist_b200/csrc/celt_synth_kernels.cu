@@ -149,12 +149,18 @@ __device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *fram
 
 // ------------------------------------------------------------ long frame ---
 // One stereo (or mono: nch == 1) long block per call.  See file header.
-template <int kMode>
+template <int kModeT>
 __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off,
                                            int cb, int nch, bool store, bool more, long long fnext,
-                                           const float (&w4)[4], GroupCtx &grp)
+                                           const float (&w4)[4], GroupCtx &grp, int vmask)
 {
+    // vmask (group mode): bit ch set = channel ch of this warp is a long block in this frame.  Two
+    // mono streams that share a warp switch blocks independently; when they disagree the frame is
+    // run through long_frame and short_frame once each and each keeps only its own channel.
+    constexpr bool kPaired = kModeT == kModeGroupPaired;
+    constexpr int kMode = kPaired ? kModeGroup : kModeT;
     constexpr bool kStereo = kMode == kModeStereo;
+    if (!kPaired) vmask = 3;
     constexpr float pre_re[30] = {NQ_PRE30_RE};
     constexpr float pre_im[30] = {NQ_PRE30_IM};
     constexpr float post_re[16] = {NQ_POST16_RE};
@@ -229,7 +235,7 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
         if (ch < nch) {
-            if (active)   // raw tail for the next frame: y[900+2k1], y[901+2k1]
+            if (active && (!kPaired || ((vmask >> ch) & 1)))   // raw tail for the next frame: y[900+2k1], y[901+2k1]
                 *reinterpret_cast<float2 *>(ws.tail + ch * kHalfOvl + 2 * k1) = make_float2(E[ch][15], O[ch][15]);
             // TDAC mirror with the previous raw tail [mdct.c:361-377]; m = 2k1 and 2k1+1
             const float t0 = told[ch].y, t1 = told[ch].x;   // tail[59-2k1], tail[58-2k1]
@@ -250,10 +256,21 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
         } else if (kMode == kModeGroup) {
             // the frame as a [960][2] plane in the (now idle) transpose buffer; column 1 of a mono stream is unused
             float4 *pl = reinterpret_cast<float4 *>(ws.x);
-            if (nch == 2) {
+            if (nch == 2 && vmask == 3) {
                 pl[29 - k1] = make_float4(H0[0], H0[1], H1[0], H1[1]);
 #pragma unroll
                 for (int k2 = 0; k2 < 15; k2++) pl[30 + k1 + 30 * k2] = make_float4(E[0][k2], E[1][k2], O[0][k2], O[1][k2]);
+            } else if (nch == 2) {   // only one column is this pass's to write
+                const bool second = vmask == 2;
+                float *col = reinterpret_cast<float *>(ws.x) + (second ? 1 : 0);
+                col[2 * (58 - 2 * k1)] = second ? H0[1] : H0[0];
+                col[2 * (59 - 2 * k1)] = second ? H1[1] : H1[0];
+#pragma unroll
+                for (int k2 = 0; k2 < 15; k2++) {
+                    const int n = 60 + 2 * (k1 + 30 * k2);
+                    col[2 * n] = second ? E[1][k2] : E[0][k2];
+                    col[2 * n + 2] = second ? O[1][k2] : O[0][k2];
+                }
             } else {
                 pl[29 - k1] = make_float4(H0[0], 0.f, H1[0], 0.f);
 #pragma unroll
@@ -299,16 +316,19 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
 // ------------------------------------------------------ transient frame ----
 // 8 short blocks per channel (N = 240, N2 = 120, N4 = 60), sub-block b uses
 // coefficients X[b + 8j] (celt_decoder_clean.c:292-300).
-template <int kMode>
+template <int kModeT>
 __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off,
-                                            int cb, int nch, bool store, bool more, long long fnext, GroupCtx &grp)
+                                            int cb, int nch, bool store, bool more, long long fnext, GroupCtx &grp, int vmask)
 {
+    constexpr bool kPaired = kModeT == kModeGroupPaired;
+    constexpr int kMode = kPaired ? kModeGroup : kModeT;
     constexpr bool kStereo = kMode == kModeStereo;
     constexpr float pre_re[30] = {NQ_PRE30_RE};
     constexpr float pre_im[30] = {NQ_PRE30_IM};
 
     // lane = (channel c, sub-block b, half h); bins i = 2*n1 + h
     const int c = lane >> 4, b = (lane >> 1) & 7, h = lane & 1;
+    const bool mine = !kPaired || ((vmask >> c) & 1);   // see long_frame: bit c = this channel is transient here
     float2 g[30];
     {
         const float *row = ws.in + c * kInRowFloats + b;
@@ -360,11 +380,13 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
         const float wlo = tb.window[59 - m], whi = tb.window[60 + m];
         const float olo = fmaf(whi, tp, -(wlo * head[k1]));   // out[59-m]
         const float ohi = fmaf(wlo, tp, whi * head[k1]);      // out[60+m]
-        stage[(120 * b + 59 - m) * 2 + c] = olo;
-        stage[(120 * b + 60 + m) * 2 + c] = ohi;
+        if (mine) {
+            stage[(120 * b + 59 - m) * 2 + c] = olo;
+            stage[(120 * b + 60 + m) * 2 + c] = ohi;
+        }
     }
     __syncwarp();   // old frame tail fully consumed, staging complete
-    if (b == 7) {
+    if (b == 7 && mine) {
 #pragma unroll
         for (int k1 = 0; k1 < 30; k1++) {
             const int m = h ? 59 - 2 * k1 : 2 * k1;
@@ -402,18 +424,19 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
 // mdct_backward_generic_kernel below -- and leaves the frame as a [N][2] plane at the start of
 // ws.x.  What matters is that such frames can sit anywhere inside a batch and hand their tail on.
 __device__ __noinline__ void small_frame_planes(const GenericTables *gt, const float *win, float *in_rows, float2 *xbuf,
-                                                float *tails, int lane, int nch, int sh, int is_tr)
+                                                float *tails, int lane, int nch, int sh, int trmask)
 {
     const int Nf = kFrame >> sh;
-    const int nb = is_tr ? (8 >> sh) : 1;
-    const int N2 = is_tr ? 120 : Nf, N4 = N2 >> 1, R = N4 / 30;
-    const int shift = is_tr ? 3 : sh;
-    const float sine = (float)2 * 3.141592653f * (.125f) / (float)(kMdctN >> shift);   // mdct.c:292
     float *plane = reinterpret_cast<float *>(xbuf);   // [Nf][2], at most 480 x 2 floats
     float2 *a_buf = xbuf + 480, *b_buf = a_buf + 240;
     float *y = reinterpret_cast<float *>(a_buf);      // y[N2] takes a_buf's place once stage 1 has read it
     const float *trig = gt->trig;
     for (int ch = 0; ch < nch; ch++) {
+        const int is_tr = (trmask >> ch) & 1;         // bit ch: channel ch uses short blocks in this frame
+        const int nb = is_tr ? (8 >> sh) : 1;
+        const int N2 = is_tr ? 120 : Nf, N4 = N2 >> 1, R = N4 / 30;
+        const int shift = is_tr ? 3 : sh;
+        const float sine = (float)2 * 3.141592653f * (.125f) / (float)(kMdctN >> shift);   // mdct.c:292
         const float *row = in_rows + ch * kInRowFloats;
         float *tail = tails + ch * kHalfOvl;
         for (int b = 0; b < nb; b++) {
@@ -471,9 +494,14 @@ __device__ __noinline__ void small_frame_planes(const GenericTables *gt, const f
 // 128 to 168 per thread, which the group variant needs to stay out of local memory.
 // kAnySize: the batch may hold frames shorter than 20 ms (p.frame_offset != nullptr).  A separate
 // instantiation, so that the common all-20-ms kernel keeps its register allocation.
-template <int kMode, int kWarps, bool kAnySize>
+template <int kModeT, int kWarps, bool kAnySize>
 __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid_constant__ SynthParams p)
 {
+    // kModeGroupPaired = kModeGroup + warps that carry two mono streams with independent block
+    // switching (the masked two-pass path); a separate instantiation keeps that code out of the
+    // plain group kernel, which measurably pays for it otherwise.
+    constexpr bool kPaired = kModeT == kModeGroupPaired;
+    constexpr int kMode = kPaired ? kModeGroup : kModeT;
     constexpr bool kStereo = kMode == kModeStereo;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastTables &tb = *reinterpret_cast<FastTables *>(smem_raw);
@@ -543,14 +571,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
     uint32_t phase = 0;
     for (; item < nitems; item += item_stride) {
         long long run;
-        int cb, nch, flag_col, halo_bit;
+        int cb, nch, flag_col, halo_bit, flag_col1 = -1;
         if (kMode == kModeGroup) {
             const StreamDesc sd = p.streams[slot];
             run = item;
             cb = sd.row;
             nch = sd.nch;
             flag_col = sd.flag_col;
-            halo_bit = p.flag_per_stream ? slot : 0;
+            halo_bit = sd.flag_col;
+            if (kPaired && sd.flag_col1 != sd.flag_col) flag_col1 = sd.flag_col1;   // two mono streams in one warp
         } else {
             run = kStereo ? item : item / p.npairs;
             const int pair = kStereo ? 0 : int(item - run * p.npairs);
@@ -582,24 +611,40 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         }
         // flag byte of a frame: bit 0 = transient (short blocks), bits 1-2 = 3 - LM (0: 20 ms frame)
         int flag = f < 0 ? (p.halo_lm_shift << 1) | ((p.halo_transient >> halo_bit) & 1) : flags[f * p.flag_stride];
+        // transient bit of the second channel when it is a stream of its own
+        int tr1 = -1;
+        if (kPaired && flag_col1 >= 0)
+            tr1 = f < 0 ? (p.halo_transient >> flag_col1) & 1 : p.transient[f * p.flag_stride + flag_col1] & 1;
         for (; f < f1; f++) {
             const bool more = f + 1 < f1;
             const int next_flag = more ? flags[(f + 1) * p.flag_stride] : 0;
+            int next_tr1 = -1;
+            if (kPaired && flag_col1 >= 0 && more) next_tr1 = p.transient[(f + 1) * p.flag_stride + flag_col1] & 1;
             while (!mbar_try_wait(&ws.bar, phase)) {}
             phase ^= 1;
             const bool store = f >= f0;
             const long long off = (kAnySize && store) ? p.frame_offset[f] : f * kFrame;
             const int sh = kAnySize ? (flag >> 1) & 3 : 0;
             int niter = grp.niter;
+            const int tr0 = flag & 1;
+            const bool split = kPaired && tr1 >= 0 && tr1 != tr0;
             if (sh == 0) {
-                if (!(flag & 1)) long_frame<kMode>(p, tb, ws, lane, off, cb, nch, store, more, f + 1, w4, grp);
-                else short_frame<kMode>(p, tb, ws, lane, off, cb, nch, store, more, f + 1, grp);
+                // one pass, or (two mono streams that disagree) a long pass for the one and a short
+                // pass for the other; the long pass goes first because it needs ws.x as its transpose
+                // buffer, and only the last pass may release ws.in to the prefetch
+                for (int ps = 0; ps < (kPaired && split ? 2 : 1); ps++) {
+                    const bool is_short = split ? ps == 1 : tr0 != 0;
+                    const int vmask = !(kPaired && split) ? 3 : ((ps == 1) == (tr0 != 0) ? 1 : 2);
+                    const bool pmore = more && (!split || ps == 1);
+                    if (!is_short) long_frame<kModeT>(p, tb, ws, lane, off, cb, nch, store, pmore, f + 1, w4, grp, vmask);
+                    else short_frame<kModeT>(p, tb, ws, lane, off, cb, nch, store, pmore, f + 1, grp, vmask);
+                }
             } else {
                 if (kMode == kModeGroup && grp.pending) {   // see long_frame
                     group_sync(grp);
                     grp.pending = false;
                 }
-                small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, nch, sh, flag & 1);
+                small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
                 if (more && lane == 0) {   // ws.in fully consumed: prefetch the next frame
                     mbar_expect_tx(&ws.bar, nch * kFrame * 4);
                     for (int ch = 0; ch < nch; ch++)
@@ -631,6 +676,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                 grp.pending = true;   // ... and must stay intact until the whole group is through this pass
             }
             flag = next_flag;
+            tr1 = next_tr1;
         }
         __syncwarp();
         if (f1 == p.nframes && p.tail_out != nullptr) {
@@ -684,6 +730,8 @@ cudaError_t prepare_kernels()
     cudaError_t e = prepare_variant<kModeStereo, kWarpsPerCta>(smem);
     if (e == cudaSuccess) e = prepare_variant<kModeGroup, kWarpsPerCta>(smem);
     if (e == cudaSuccess) e = prepare_variant<kModeGroup, 12>(smem);
+    if (e == cudaSuccess) e = prepare_variant<kModeGroupPaired, kWarpsPerCta>(smem);
+    if (e == cudaSuccess) e = prepare_variant<kModeGroupPaired, 12>(smem);
     if (e == cudaSuccess) e = prepare_variant<kModeDirect, kWarpsPerCta>(smem);
     return e;
 }
@@ -699,10 +747,12 @@ cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream
 {
     long long per_cta = kWarpsPerCta, nitems = p.nruns * p.npairs;
     int warps = kWarpsPerCta;
+    bool paired = false;
     if (mode == kModeGroup) {
         per_cta = groups_per_cta(p.nstreams);
         nitems = p.nruns;
         warps = group_cta_warps(p.nstreams);
+        for (int s = 0; s < p.nstreams; s++) paired = paired || p.streams[s].flag_col1 != p.streams[s].flag_col;
     }
     long long ctas = (nitems + per_cta - 1) / per_cta;
     if (ctas > num_sms) ctas = num_sms;   // persistent: one CTA per SM, warps stride over the items
@@ -711,6 +761,8 @@ cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream
     const size_t smem = sizeof(FastTables) + (size_t)warps * sizeof(WarpSmem);
     const unsigned grid = (unsigned)ctas;
     if (mode == kModeStereo) launch_variant<kModeStereo, kWarpsPerCta>(p, grid, smem, stream);
+    else if (mode == kModeGroup && paired && warps == 12) launch_variant<kModeGroupPaired, 12>(p, grid, smem, stream);
+    else if (mode == kModeGroup && paired) launch_variant<kModeGroupPaired, kWarpsPerCta>(p, grid, smem, stream);
     else if (mode == kModeGroup && warps == 12) launch_variant<kModeGroup, 12>(p, grid, smem, stream);
     else if (mode == kModeGroup) launch_variant<kModeGroup, kWarpsPerCta>(p, grid, smem, stream);
     else launch_variant<kModeDirect, kWarpsPerCta>(p, grid, smem, stream);

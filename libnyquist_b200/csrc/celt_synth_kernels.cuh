@@ -42,14 +42,17 @@ struct GenericTables {
 //                output channel c from decoded channel mapping[c] (opus_multistream_decoder.c:260-299);
 //   kModeDirect  more streams than a CTA has warps: channel pairs, scattered stores (slow, rare).
 constexpr int kModeStereo = 0, kModeGroup = 1, kModeDirect = 2;
+constexpr int kModeGroupPaired = 3;   // kernel-internal: kModeGroup whose warps may carry two independent mono streams
 constexpr int kMaxGroupStreams = kWarpsPerCta;
 constexpr int kMaxChannels = 255;
 
+// One warp of a group: a coupled stream, a mono stream, or TWO consecutive mono streams (their
+// rows are adjacent; each keeps its own transient flag).
 struct StreamDesc {
-    uint8_t nch;        // 2: coupled stream, 1: mono stream
-    uint8_t row;        // first decoded channel (coefficient row inside a frame)
-    uint8_t flag_col;   // column of the transient flag inside a frame's flag record
-    uint8_t pad_;
+    uint8_t nch;         // channels this warp synthesises (1 or 2)
+    uint8_t row;         // first decoded channel (coefficient row inside a frame)
+    uint8_t flag_col;    // column of channel 0's flag inside a frame's flag record
+    uint8_t flag_col1;   // column of channel 1's flag (== flag_col for a coupled stream)
 };
 
 struct SynthParams {
@@ -68,7 +71,7 @@ struct SynthParams {
     int D;                      // decoded channels per frame (coefficient rows)
     int C;                      // output channels (pcm row width); == D without a channel mapping
     int npairs;                 // kModeDirect: channel pairs per frame
-    int nstreams;               // kModeGroup: warps per group
+    int nstreams;               // kModeGroup: warps per group (coupled streams + pairs of mono streams)
     int store_threads;          // kModeGroup: threads of a group in the store pass (group_store_threads())
     int halo_lm_shift;          // 3 - LM of the halo frame
     int halo_transient;         // flag(s) of the halo frame: bit s = stream s (bit 0 for everybody if !flag_per_stream)

@@ -187,6 +187,8 @@ MS_LAYOUTS = {
     "surround_7.1": (5, 3, [0, 6, 1, 2, 3, 4, 5, 7]),
     "dual_mono_muted_dup": (3, 1, [2, 255, 0, 0, 1, 3, 3]),
     "fourteen_mono": (14, 0, list(range(14))),
+    "five_mono_odd": (5, 0, [4, 3, 2, 1, 0]),
+    "max_warps_13_coupled_2_mono": (15, 13, list(range(28))),
 }
 
 
@@ -221,8 +223,9 @@ def test_multistream_rejects_bad_layouts(synth):
     with pytest.raises(nq.NqError):
         synth.synth_batch_ms_torch(coef, tr, 2, 1, [0, 1, 3])        # decoded channel 3 does not exist
     with pytest.raises(nq.NqError) as e:
-        synth.synth_batch_ms_torch(torch.zeros((4, 15, 960), device="cuda"),
-                                   torch.zeros((4, 15), dtype=torch.uint8, device="cuda"), 15, 0, list(range(15)))
+        # 29 mono streams = 15 warps (mono streams pair up): one more than a CTA has
+        synth.synth_batch_ms_torch(torch.zeros((4, 29, 960), device="cuda"),
+                                   torch.zeros((4, 29), dtype=torch.uint8, device="cuda"), 29, 0, list(range(29)))
     assert e.value.code == -5
 
 

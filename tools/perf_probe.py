@@ -26,6 +26,29 @@ def run(synth, frames, C, p_tr, steps=5):
     return dict(frames=frames, C=C, p_transient=p_tr, ms=round(ms, 3), GBps=round(gbs, 1),
                 Mframes_per_s=round(frames / ms / 1e3, 2), frac_of_6527=round(gbs / 6527.5, 3))
 
+def run_ms(synth, frames, streams, coupled, p_tr, steps=5):
+    """Multistream layout (own transient flag per stream), identity channel mapping."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    D = streams + coupled
+    coef = torch.empty((frames, D, 960), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g)
+    tr = (torch.rand((frames, streams), generator=g, device=dev) < p_tr).to(torch.uint8)
+    pcm = torch.empty((frames * 960, D), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        synth.synth_batch_ms_torch(coef, tr, streams, coupled, list(range(D)), out=pcm, want_tail=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        synth.synth_batch_ms_torch(coef, tr, streams, coupled, list(range(D)), out=pcm, want_tail=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    gbs = frames * D * 960 * 8 / (ms * 1e-3) / 1e9
+    return dict(frames=frames, streams=streams, coupled=coupled, p_transient=p_tr, ms=round(ms, 3), GBps=round(gbs, 1),
+                frac_of_6527=round(gbs / 6527.5, 3))
+
+
 if __name__ == "__main__":
     # --case frames,C,p_transient[,steps] (repeatable): run only these (used under ncu)
     cases = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--case=")]
@@ -33,7 +56,11 @@ if __name__ == "__main__":
         for c in cases:
             fr, C, p, *st = c.split(",")
             print(json.dumps(run(s, int(fr), int(C), float(p), int(st[0]) if st else 5)), flush=True)
-        if cases:
+        ms_cases = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--ms=")]
+        for c in ms_cases:   # --ms frames,streams,coupled,p_transient[,steps]
+            fr, st, cp, p, *sx = c.split(",")
+            print(json.dumps(run_ms(s, int(fr), int(st), int(cp), float(p), int(sx[0]) if sx else 5)), flush=True)
+        if cases or ms_cases:
             sys.exit(0)
         for frames, C, p in [(2_000_000, 2, 0.0), (2_000_000, 2, 0.028), (2_000_000, 2, 0.2), (2_000_000, 2, 1.0),
                              (4_000_000, 1, 0.028), (500_000, 8, 0.028), (500_000, 8, 0.2), (1_300_000, 3, 0.028), (700_000, 6, 0.028),
