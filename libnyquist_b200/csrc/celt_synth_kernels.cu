@@ -152,8 +152,12 @@ __device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *fram
 template <int kModeT>
 __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off,
                                            int cb, int nch, bool store, bool more, long long fnext,
-                                           const float (&w4)[4], GroupCtx &grp, int vmask)
+                                           const float (&w4)[4], GroupCtx &grp, int vmask, int next_nch)
 {
+    // kModeMono: the two "channels" are two CONSECUTIVE FRAMES of one mono stream (rows f and f+1
+    // of the coefficient array), so a mono stream fills the warp like a stereo one; channel 1 then
+    // overlap-adds against channel 0's fresh tail instead of a stored one.  next_nch = rows to
+    // prefetch for the next item (1 or 2 frames there; == nch in every other mode).
     // vmask (group mode): bit ch set = channel ch of this warp is a long block in this frame.  Two
     // mono streams that share a warp switch blocks independently; when they disagree the frame is
     // run through long_frame and short_frame once each and each keeps only its own channel.
@@ -197,8 +201,8 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
     __syncwarp();
     // every lane has consumed its part of ws.in: prefetch the next frame
     if (more && lane == 0) {
-        mbar_expect_tx(&ws.bar, nch * kFrame * 4);
-        for (int ch = 0; ch < nch; ch++) {
+        mbar_expect_tx(&ws.bar, next_nch * kFrame * 4);
+        for (int ch = 0; ch < next_nch; ch++) {
             const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + (cb + ch) * kFrame;
             tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
         }
@@ -212,7 +216,7 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
         if (ch < nch) {
-            told[ch] = *reinterpret_cast<const float2 *>(ws.tail + ch * kHalfOvl + 58 - 2 * k1);
+            told[ch] = *reinterpret_cast<const float2 *>(ws.tail + (kMode == kModeMono ? 0 : ch * kHalfOvl) + 58 - 2 * k1);
             float2 z[16];
             const float2 *src = ws.x + ch * kXChanF2 + k1;
 #pragma unroll
@@ -232,10 +236,17 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
         }
     }
     __syncwarp();   // all lanes are done with ws.x and with the old tail
+    if (kMode == kModeMono && nch == 2) {
+        // frame f+1 mirrors against frame f's raw tail: tail[58-2k1], tail[59-2k1] sit in lane 29-k1
+        told[1].x = __shfl_sync(kFull, E[0][15], (29 - lane) & 31);
+        told[1].y = __shfl_sync(kFull, O[0][15], (29 - lane) & 31);
+    }
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
         if (ch < nch) {
-            if (active && (!kPaired || ((vmask >> ch) & 1)))   // raw tail for the next frame: y[900+2k1], y[901+2k1]
+            if (kMode == kModeMono) {   // one stream: only the LAST frame's tail is kept, in slot 0
+                if (active && ch == nch - 1) *reinterpret_cast<float2 *>(ws.tail + 2 * k1) = make_float2(E[ch][15], O[ch][15]);
+            } else if (active && (!kPaired || ((vmask >> ch) & 1)))   // raw tail for the next frame: y[900+2k1], y[901+2k1]
                 *reinterpret_cast<float2 *>(ws.tail + ch * kHalfOvl + 2 * k1) = make_float2(E[ch][15], O[ch][15]);
             // TDAC mirror with the previous raw tail [mdct.c:361-377]; m = 2k1 and 2k1+1
             const float t0 = told[ch].y, t1 = told[ch].x;   // tail[59-2k1], tail[58-2k1]
@@ -253,6 +264,18 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
 #pragma unroll
             for (int k2 = 0; k2 < 15; k2++)
                 __stcs(dst + 30 + k1 + 30 * k2, make_float4(E[0][k2], E[1][k2], O[0][k2], O[1][k2]));
+        } else if (kMode == kModeMono) {
+            // frame f (+ frame f+1): each lane owns y[2k], y[2k+1] -> 8-byte stores, 240 contiguous bytes per instruction
+            float *dst = p.pcm + off;
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch < nch) {
+                    __stcs(reinterpret_cast<float2 *>(dst + ch * kFrame + 58 - 2 * k1), make_float2(H0[ch], H1[ch]));
+#pragma unroll
+                    for (int k2 = 0; k2 < 15; k2++)
+                        __stcs(reinterpret_cast<float2 *>(dst + ch * kFrame + 60 + 2 * (k1 + 30 * k2)), make_float2(E[ch][k2], O[ch][k2]));
+                }
+            }
         } else if (kMode == kModeGroup) {
             // the frame as a [960][2] plane in the (now idle) transpose buffer; column 1 of a mono stream is unused
             float4 *pl = reinterpret_cast<float4 *>(ws.x);
@@ -318,7 +341,8 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
 // coefficients X[b + 8j] (celt_decoder_clean.c:292-300).
 template <int kModeT>
 __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off,
-                                            int cb, int nch, bool store, bool more, long long fnext, GroupCtx &grp, int vmask)
+                                            int cb, int nch, bool store, bool more, long long fnext, GroupCtx &grp, int vmask,
+                                            int next_nch)
 {
     constexpr bool kPaired = kModeT == kModeGroupPaired;
     constexpr int kMode = kPaired ? kModeGroup : kModeT;
@@ -360,8 +384,8 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
     }
     __syncwarp();
     if (more && lane == 0) {
-        mbar_expect_tx(&ws.bar, nch * kFrame * 4);
-        for (int ch = 0; ch < nch; ch++) {
+        mbar_expect_tx(&ws.bar, next_nch * kFrame * 4);
+        for (int ch = 0; ch < next_nch; ch++) {
             const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + (cb + ch) * kFrame;
             tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
         }
@@ -376,24 +400,32 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
     for (int k1 = 0; k1 < 30; k1++) {
         const int m = h ? 59 - 2 * k1 : 2 * k1;      // head[k1] = y[m]
         float tp = __shfl_up_sync(kFull, tl[k1], 2);  // same (c, h), sub-block b-1
-        if (b == 0) tp = ws.tail[c * kHalfOvl + 59 - m];
+        // kModeMono: c = 1 is the NEXT frame of the same stream; its block 0 follows block 7 of c = 0 (lane - 2)
+        if (b == 0 && (kMode != kModeMono || c == 0)) tp = ws.tail[(kMode == kModeMono ? 0 : c * kHalfOvl) + 59 - m];
         const float wlo = tb.window[59 - m], whi = tb.window[60 + m];
         const float olo = fmaf(whi, tp, -(wlo * head[k1]));   // out[59-m]
         const float ohi = fmaf(wlo, tp, whi * head[k1]);      // out[60+m]
-        if (mine) {
+        if (kMode == kModeMono) {   // planar: frame c at stage[960 c ..]
+            stage[kFrame * c + 120 * b + 59 - m] = olo;
+            stage[kFrame * c + 120 * b + 60 + m] = ohi;
+        } else if (mine) {
             stage[(120 * b + 59 - m) * 2 + c] = olo;
             stage[(120 * b + 60 + m) * 2 + c] = ohi;
         }
     }
     __syncwarp();   // old frame tail fully consumed, staging complete
-    if (b == 7 && mine) {
+    if (b == 7 && (kMode == kModeMono ? c == nch - 1 : mine)) {
 #pragma unroll
         for (int k1 = 0; k1 < 30; k1++) {
             const int m = h ? 59 - 2 * k1 : 2 * k1;
-            ws.tail[c * kHalfOvl + 59 - m] = tl[k1];          // y_7[60 + (59-m)]
+            ws.tail[(kMode == kModeMono ? 0 : c * kHalfOvl) + 59 - m] = tl[k1];          // y_7[60 + (59-m)]
         }
     }
-    if (store && kMode != kModeGroup) {   // group mode: `stage` IS the stream's plane, stored by the group
+    if (store && kMode == kModeMono) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+        float4 *dst = reinterpret_cast<float4 *>(p.pcm + off);
+        for (int j = lane; j < nch * (kFrame / 4); j += 32) __stcs(dst + j, s4[j]);
+    } else if (store && kMode != kModeGroup) {   // group mode: `stage` IS the stream's plane, stored by the group
         if (kStereo) {
             const float4 *s4 = reinterpret_cast<const float4 *>(stage);
             float4 *dst = reinterpret_cast<float4 *>(p.pcm + off * 2);
@@ -602,22 +634,32 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         __syncwarp();
         long long f = warm ? f0 - 1 : f0;
         const uint8_t *flags = p.transient + flag_col;
-        if (lane == 0) {
-            mbar_expect_tx(&ws.bar, nch * kFrame * 4);
-            for (int ch = 0; ch < nch; ch++) {
-                const float *src = (f < 0 ? p.halo_coef : p.coef + f * p.D * kFrame) + (cb + ch) * kFrame;
-                tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
-            }
-        }
         // flag byte of a frame: bit 0 = transient (short blocks), bits 1-2 = 3 - LM (0: 20 ms frame)
         int flag = f < 0 ? (p.halo_lm_shift << 1) | ((p.halo_transient >> halo_bit) & 1) : flags[f * p.flag_stride];
         // transient bit of the second channel when it is a stream of its own
         int tr1 = -1;
         if (kPaired && flag_col1 >= 0)
             tr1 = f < 0 ? (p.halo_transient >> flag_col1) & 1 : p.transient[f * p.flag_stride + flag_col1] & 1;
-        for (; f < f1; f++) {
-            const bool more = f + 1 < f1;
-            const int next_flag = more ? flags[(f + 1) * p.flag_stride] : 0;
+        // kModeMono: an item is one frame, or two consecutive 20 ms frames of the same block type
+        // (never the warm-up frame, whose output is not stored); nfr = frames of the current item
+        auto mono_pair = [&](long long g, int gflag) -> bool {
+            return kMode == kModeMono && g >= f0 && g + 1 < f1 && (gflag >> 1) == 0 && flags[(g + 1) * p.flag_stride] == gflag;
+        };
+        int nfr = (kMode == kModeMono && mono_pair(f, flag)) ? 2 : 1;
+        const int state_nch = nch;   // channels with a tail of their own (kModeMono: nch is reused as frames per item)
+        if (lane == 0) {
+            const int rows = kMode == kModeMono ? nfr : nch;
+            mbar_expect_tx(&ws.bar, rows * kFrame * 4);
+            for (int ch = 0; ch < rows; ch++) {
+                const float *src = (f < 0 ? p.halo_coef : p.coef + f * p.D * kFrame) + (cb + ch) * kFrame;
+                tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
+            }
+        }
+        while (f < f1) {
+            if (kMode == kModeMono) nch = nfr;
+            const bool more = f + nfr < f1;
+            const int next_flag = more ? flags[(f + nfr) * p.flag_stride] : 0;
+            const int next_nfr = (kMode == kModeMono && more && mono_pair(f + nfr, next_flag)) ? 2 : 1;
             int next_tr1 = -1;
             if (kPaired && flag_col1 >= 0 && more) next_tr1 = p.transient[(f + 1) * p.flag_stride + flag_col1] & 1;
             while (!mbar_try_wait(&ws.bar, phase)) {}
@@ -636,8 +678,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                     const bool is_short = split ? ps == 1 : tr0 != 0;
                     const int vmask = !(kPaired && split) ? 3 : ((ps == 1) == (tr0 != 0) ? 1 : 2);
                     const bool pmore = more && (!split || ps == 1);
-                    if (!is_short) long_frame<kModeT>(p, tb, ws, lane, off, cb, nch, store, pmore, f + 1, w4, grp, vmask);
-                    else short_frame<kModeT>(p, tb, ws, lane, off, cb, nch, store, pmore, f + 1, grp, vmask);
+                    const int next_nch = kMode == kModeMono ? next_nfr : nch;
+                    if (!is_short) long_frame<kModeT>(p, tb, ws, lane, off, cb, nch, store, pmore, f + nfr, w4, grp, vmask, next_nch);
+                    else short_frame<kModeT>(p, tb, ws, lane, off, cb, nch, store, pmore, f + nfr, grp, vmask, next_nch);
                 }
             } else {
                 if (kMode == kModeGroup && grp.pending) {   // see long_frame
@@ -646,8 +689,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                 }
                 small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
                 if (more && lane == 0) {   // ws.in fully consumed: prefetch the next frame
-                    mbar_expect_tx(&ws.bar, nch * kFrame * 4);
-                    for (int ch = 0; ch < nch; ch++)
+                    const int next_nch = kMode == kModeMono ? next_nfr : nch;
+                    mbar_expect_tx(&ws.bar, next_nch * kFrame * 4);
+                    for (int ch = 0; ch < next_nch; ch++)
                         tma_load_row(ws.in + ch * kInRowFloats, p.coef + (f + 1) * p.D * kFrame + (cb + ch) * kFrame, kFrame * 4, &ws.bar);
                 }
                 const int Nf = kFrame >> sh;
@@ -677,12 +721,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             }
             flag = next_flag;
             tr1 = next_tr1;
+            f += nfr;
+            nfr = next_nfr;
         }
         __syncwarp();
         if (f1 == p.nframes && p.tail_out != nullptr) {
             for (int i = lane; i < 2 * kHalfOvl; i += 32) {
                 const int ch = i / kHalfOvl;
-                if (ch < nch) p.tail_out[(cb + ch) * kHalfOvl + (i - ch * kHalfOvl)] = ws.tail[i];
+                if (ch < state_nch) p.tail_out[(cb + ch) * kHalfOvl + (i - ch * kHalfOvl)] = ws.tail[i];
             }
         }
         __syncwarp();
@@ -712,6 +758,7 @@ int group_store_threads(int C, int nstreams)
 int synth_mode(int D, int C, int nstreams, bool identity_map)
 {
     if (D == 2 && C == 2 && nstreams == 1 && identity_map) return kModeStereo;
+    if (D == 1 && C == 1 && identity_map) return kModeMono;
     if (nstreams <= kMaxGroupStreams && group_store_threads(C, nstreams) > 0) return kModeGroup;
     return kModeDirect;
 }
@@ -733,6 +780,7 @@ cudaError_t prepare_kernels()
     if (e == cudaSuccess) e = prepare_variant<kModeGroupPaired, kWarpsPerCta>(smem);
     if (e == cudaSuccess) e = prepare_variant<kModeGroupPaired, 12>(smem);
     if (e == cudaSuccess) e = prepare_variant<kModeDirect, kWarpsPerCta>(smem);
+    if (e == cudaSuccess) e = prepare_variant<kModeMono, kWarpsPerCta>(smem);
     return e;
 }
 
@@ -761,6 +809,7 @@ cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream
     const size_t smem = sizeof(FastTables) + (size_t)warps * sizeof(WarpSmem);
     const unsigned grid = (unsigned)ctas;
     if (mode == kModeStereo) launch_variant<kModeStereo, kWarpsPerCta>(p, grid, smem, stream);
+    else if (mode == kModeMono) launch_variant<kModeMono, kWarpsPerCta>(p, grid, smem, stream);
     else if (mode == kModeGroup && paired && warps == 12) launch_variant<kModeGroupPaired, 12>(p, grid, smem, stream);
     else if (mode == kModeGroup && paired) launch_variant<kModeGroupPaired, kWarpsPerCta>(p, grid, smem, stream);
     else if (mode == kModeGroup && warps == 12) launch_variant<kModeGroup, 12>(p, grid, smem, stream);

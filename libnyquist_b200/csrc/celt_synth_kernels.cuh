@@ -40,8 +40,11 @@ struct GenericTables {
 //                leaves its frame as a [960][2] plane in shared memory and the group then writes
 //                the interleaved [960][C] output frame with contiguous float4 stores, gathering
 //                output channel c from decoded channel mapping[c] (opus_multistream_decoder.c:260-299);
-//   kModeDirect  more streams than a CTA has warps: channel pairs, scattered stores (slow, rare).
+//   kModeDirect  more streams than a CTA has warps: channel pairs, scattered stores (slow, rare);
+//   kModeMono    D = C = 1: one warp per run like stereo, its two "channels" being two consecutive
+//                frames of the stream whenever they have the same block type.
 constexpr int kModeStereo = 0, kModeGroup = 1, kModeDirect = 2;
+constexpr int kModeMono = 4;
 constexpr int kModeGroupPaired = 3;   // kernel-internal: kModeGroup whose warps may carry two independent mono streams
 constexpr int kMaxGroupStreams = kWarpsPerCta;
 constexpr int kMaxChannels = 255;
