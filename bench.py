@@ -41,7 +41,7 @@ E2E_FRAMES = 262_144                      # host-buffer leg: 2 GB in + 2 GB out 
 FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of celt_synth_kernel<true> from the
 # committed ncu capture (profiles/), scaled to bytes per frame; None until a capture exists.
-NCU_TRAFFIC_BYTES_PER_FRAME = 15340.2    # profiles/r1_ncu_full_celt_synth_kernel_1Mframes.csv: (7.703919 + 7.636280) GB / 1e6 frames
+NCU_TRAFFIC_BYTES_PER_FRAME = 15362.1    # profiles/r1b_full_stereo10M.csv (the bench's own 10 M-frame launch): (76.864032 + 76.757152) GB / 1e7 frames
 
 
 def workload_name(frames):
@@ -409,7 +409,7 @@ def main():
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None if NCU_TRAFFIC_BYTES_PER_FRAME is None else NCU_TRAFFIC_BYTES_PER_FRAME * frames,
-        "kernel": "nq::celt_synth_kernel<true>", "algorithmic_bytes_per_launch": frames * BYTES_PER_FRAME,
+        "kernel": "nq::celt_synth_kernel<kModeStereo, 14 warps, 20 ms frames>", "algorithmic_bytes_per_launch": frames * BYTES_PER_FRAME,
         "launch_ms": kernel_ms, "peak_source": peak_src,
     }
     line = {
