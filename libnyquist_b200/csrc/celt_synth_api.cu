@@ -232,6 +232,15 @@ int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const ui
             sd.flag_col = (uint8_t)(L.per_stream_flags ? s0 : 0);
             sd.flag_col1 = (uint8_t)(L.per_stream_flags && sd.nch == 2 ? s0 + 1 : sd.flag_col);
         }
+        // store-pass loop shape (celt_synth_kernels.cu group_store_frame): every float4 of an output
+        // row = two coupled streams' (L, R) in order -> vector loads; any silent channel -> masked loop
+        bool vec = L.C % 4 == 0, muted = false;
+        for (int c = 0; c < L.C; c++) muted = muted || L.mapping[c] == 255;
+        for (int c = 0; c + 1 < L.C && vec; c += 2) {
+            const int d = L.mapping[c];
+            vec = d != 255 && d < 2 * L.coupled && (d & 1) == 0 && L.mapping[c + 1] == d + 1;
+        }
+        p.store_shape = muted ? 2 : (vec ? 0 : 1);
         for (int c = 0; c < L.C; c++) {
             const int d = L.mapping[c];
             if (d == 255) p.chan_src[c] = 0xffffu;   // muted channel, opus_multistream_decoder.c:291-299

@@ -106,6 +106,7 @@ struct GroupCtx {
     int q0, T2, niter;     // first float4, stride, iterations (0 for the threads beyond T2)
     int T, bar_id;         // threads in the group, its named barrier (1..15)
     unsigned mute;         // bit j: element j belongs to a silent output channel
+    int shape;             // store-loop shape, see group_store_frame (uniform over the group)
     bool pending;          // the previous frame's store pass may still be reading the planes
 };
 
@@ -121,29 +122,50 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
 
 // Interleaved output frame [960][C] from the group's planes: output channel c is decoded
-// channel mapping[c] (a gather, opus_multistream_decoder.c:260-299) or silence.
+// channel mapping[c] (a gather, opus_multistream_decoder.c:260-299) or silence.  Three loop
+// shapes, chosen once per kernel: both element pairs of a thread are the two channels of one
+// coupled stream in order (plain layouts: 2 x LDS.64), the general gather (4 x LDS.32), and the
+// general gather with silent channels.
 __device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *frame_out, int niter)
 {
     float4 *dst = reinterpret_cast<float4 *>(frame_out) + g.q0;
     uint32_t a0 = g.src[0], a1 = g.src[1], a2 = g.src[2], a3 = g.src[3];
+    const uint32_t step = g.step;
+    const int T2 = g.T2;
+    if (g.shape == 0) {
 #pragma unroll 5
-    for (int i = 0; i < niter; i++) {
-        float4 v;
-        v.x = lds_f32(a0);
-        v.y = lds_f32(a1);
-        v.z = lds_f32(a2);
-        v.w = lds_f32(a3);
-        if (g.mute) {
+        for (int i = 0; i < niter; i++) {
+            const float2 lo = lds_f32x2(a0), hi = lds_f32x2(a2);
+            __stcs(dst, make_float4(lo.x, lo.y, hi.x, hi.y));
+            dst += T2;
+            a0 += step; a2 += step;
+        }
+    } else if (g.shape == 1) {
+#pragma unroll 5
+        for (int i = 0; i < niter; i++) {
+            __stcs(dst, make_float4(lds_f32(a0), lds_f32(a1), lds_f32(a2), lds_f32(a3)));
+            dst += T2;
+            a0 += step; a1 += step; a2 += step; a3 += step;
+        }
+    } else {
+        for (int i = 0; i < niter; i++) {
+            float4 v = make_float4(lds_f32(a0), lds_f32(a1), lds_f32(a2), lds_f32(a3));
             if (g.mute & 1) v.x = 0.f;
             if (g.mute & 2) v.y = 0.f;
             if (g.mute & 4) v.z = 0.f;
             if (g.mute & 8) v.w = 0.f;
+            __stcs(dst, v);
+            dst += T2;
+            a0 += step; a1 += step; a2 += step; a3 += step;
         }
-        __stcs(dst, v);
-        dst += g.T2;
-        a0 += g.step; a1 += g.step; a2 += g.step; a3 += g.step;
     }
 }
 
@@ -592,6 +614,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             grp.src[j] = sc == 0xffffu ? planes : planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + (sc & 1) * 4 + n * 8;
             if (++c == C) { c = 0; n++; }
         }
+        grp.shape = p.store_shape;
         item = (long long)blockIdx.x * G + gi;
         item_stride = (long long)gridDim.x * G;
         nitems = p.nruns;
