@@ -44,6 +44,17 @@ FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md
 NCU_TRAFFIC_BYTES_PER_FRAME = 15362.1    # profiles/r1b_full_stereo10M.csv (the bench's own 10 M-frame launch): (76.864032 + 76.757152) GB / 1e7 frames
 
 
+# Only the JSON line may reach stdout: NCCL (and anything else that writes to the C-level stdout,
+# e.g. "NCCL version ..." at communicator creation) is sent to stderr for the whole run.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def workload_name(frames):
     return (f"synthetic batch of {frames} stereo 20 ms CELT frames per GPU (2x960 f32 coefficients -> 2x960 f32 "
             f"samples, {P_TRANSIENT * 100:.1f}% transient), BASELINE.json configs[4]")
@@ -158,7 +169,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -430,7 +441,7 @@ def main():
         del coef, pcm
         torch.cuda.empty_cache()
         line["extras"] = extras(torch, np, nq, synth, dev, peak)
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
