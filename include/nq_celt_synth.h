@@ -287,6 +287,16 @@ NQ_API void cleanupCudaBuffers(void);
 NQ_API void printCudaVersion(void);
 
 /* ---- introspection for tests ------------------------------------------- */
+/* How a batch of `nframes` frames with this channel layout would be launched on
+ * a device with `num_sms` SMs (pure host code, no device needed; mapping == NULL:
+ * plain `channels`-channel batch with shared flags).  out[0] kernel variant
+ * (0 stereo, 1 group, 2 direct, 4 mono), [1] warps per group, [2] groups per CTA,
+ * [3] threads in the store pass, [4] store-loop shape, [5] mono streams paired in
+ * one warp, [6] frames per run, [7] runs, [8] post-stage CTAs, [9] of which
+ * two-channel, [10] decoded channels, [11] identity mapping.  NQ_UNIMPLEMENTED /
+ * NQ_BAD_ARG exactly where the batch entries return them. */
+NQ_API int nq_celt_debug_plan(int channels, int streams, int coupled_streams, const unsigned char *mapping,
+                              int64_t nframes, int num_sms, int64_t out[12]);
 /* Copies the host-built tables: t_long [16*31*2], t_short [2*30*2],
  * window [120], trig [481] (any pointer may be NULL). */
 NQ_API void nq_celt_debug_tables(float *t_long, float *t_short, float *window, float *trig);

@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     "nq_celt_sink_flush_pinned", "nq_celt_sink_trim_pool", "nq_celt_sink_attach", "nq_celt_sink_finish",
     "nq_clt_mdct_backward", "nq_clt_mdct_backward_B1_C2", "nq_celt_mdct_backward_host",
     "nq_compute_inv_mdcts", "nq_opus_ifft_host", "processMDCTCuda", "processMDCTCudaB1C2", "cleanupCudaBuffers",
-    "printCudaVersion", "nq_celt_debug_tables",
+    "printCudaVersion", "nq_celt_debug_tables", "nq_celt_debug_plan",
 ]
 
 
@@ -116,6 +116,7 @@ def load_library():
     L.cleanupCudaBuffers.restype = None
     L.printCudaVersion.restype = None
     L.nq_celt_debug_tables.argtypes = [fp, fp, fp, fp]
+    L.nq_celt_debug_plan.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -143,6 +144,22 @@ def debug_tables():
     trig = np.zeros(481, np.float32)
     L.nq_celt_debug_tables(_fp(t_long), _fp(t_short), _fp(window), _fp(trig))
     return dict(t_long=t_long, t_short=t_short, window=window, trig=trig)
+
+
+PLAN_FIELDS = ("mode", "warps_per_group", "groups_per_cta", "store_threads", "store_shape", "paired_mono",
+               "frames_per_run", "runs", "post_ctas", "post_ctas_two_channel", "decoded_channels", "identity")
+MODE_STEREO, MODE_GROUP, MODE_DIRECT, MODE_MONO = 0, 1, 2, 4
+
+
+def debug_plan(channels, streams=0, coupled_streams=0, mapping=None, nframes=1_000_000, num_sms=148):
+    """How a batch with this layout would be launched (pure host code, no GPU needed)."""
+    L = load_library()
+    out = (C.c_int64 * 12)()
+    mp = None if mapping is None else np.ascontiguousarray(mapping, np.uint8)
+    rc = L.nq_celt_debug_plan(int(channels), int(streams), int(coupled_streams), _vp(mp), int(nframes), int(num_sms), out)
+    if rc != NQ_OK:
+        raise NqError(rc, "nq_celt_debug_plan")
+    return dict(zip(PLAN_FIELDS, [int(v) for v in out]))
 
 
 # ---- reference-shaped single calls (host buffers, synchronous) ------------

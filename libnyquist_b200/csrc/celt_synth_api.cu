@@ -179,27 +179,14 @@ Layout plain_layout(int C)
     return L;
 }
 
-// halo_flags: bit s = transient flag of stream s of the halo frame (bit 0 for everybody without
-// per-stream flags), bits 30-31 = 3 - LM of the halo frame.
-int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8_t *transient, const float *tail_in,
-                  const float *halo_coef, unsigned halo_flags, float *pcm, float *tail_out, long long nframes,
-                  cudaStream_t stream, const long long *frame_offset = nullptr)
+void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes, bool reset, std::vector<PostJob> *jobs);
+
+// Everything about a launch that follows from the channel layout and the batch size alone: kernel
+// variant, warps per group, the streams each warp synthesises, the store pass, the runs.  Pure host
+// code (also behind nq_celt_debug_plan, so the CPU tests can check it without a device).
+int plan_layout(const Layout &L, int num_sms, long long nframes, SynthParams *pp, int *mode_out)
 {
-    const unsigned halo_transient_bits = halo_flags & 0x3fffffffu;
-    SynthParams p;
-    memset(&p, 0, sizeof p);
-    p.coef = coef;
-    p.transient = transient;
-    p.tail_in = tail_in;
-    p.halo_coef = tail_in ? nullptr : halo_coef;
-    p.halo_transient = (int)halo_transient_bits;
-    p.pcm = pcm;
-    p.tail_out = tail_out;
-    p.tables = ctx->d_fast;
-    p.gen = ctx->d_gen;
-    p.frame_offset = frame_offset;
-    p.halo_lm_shift = (int)(halo_flags >> 30);
-    p.nframes = nframes;
+    SynthParams &p = *pp;
     p.D = L.D;
     p.C = L.C;
     p.npairs = (L.D + 1) / 2;
@@ -210,14 +197,13 @@ int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const ui
     const int nmono = L.streams - L.coupled;
     const int nslots = L.coupled + (nmono + 1) / 2;
     p.nstreams = nslots;
-    const int mode = synth_mode(L.D, L.C, nslots, L.identity);
+    const int mode = *mode_out = synth_mode(L.D, L.C, nslots, L.identity, L.streams == 1);
     if (mode == kModeDirect && (!L.identity || L.per_stream_flags))
-        return fail(ctx, NQ_UNIMPLEMENTED, "a channel mapping needs at most %d coupled streams + pairs of mono streams (got %d)",
-                    kMaxGroupStreams, nslots);
-    if (L.per_stream_flags && L.streams > 30) return fail(ctx, NQ_UNIMPLEMENTED, "at most 30 streams with their own flags");
-    long long resident = (long long)ctx->num_sms * kWarpsPerCta / p.npairs;
+        return NQ_UNIMPLEMENTED;
+    if (L.per_stream_flags && L.streams > 30) return NQ_UNIMPLEMENTED;
+    long long resident = (long long)num_sms * kWarpsPerCta / p.npairs;
     if (mode == kModeGroup) {
-        resident = (long long)ctx->num_sms * groups_per_cta(nslots);
+        resident = (long long)num_sms * groups_per_cta(nslots);
         p.store_threads = group_store_threads(L.C, nslots);
         for (int s = 0; s < L.coupled; s++) {
             p.streams[s].nch = 2;
@@ -249,6 +235,35 @@ int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const ui
         }
     }
     plan_runs(nframes, resident, &p.frames_per_run, &p.nruns);
+    return NQ_OK;
+}
+
+// halo_flags: bit s = transient flag of stream s of the halo frame (bit 0 for everybody without
+// per-stream flags), bits 30-31 = 3 - LM of the halo frame.
+int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8_t *transient, const float *tail_in,
+                  const float *halo_coef, unsigned halo_flags, float *pcm, float *tail_out, long long nframes,
+                  cudaStream_t stream, const long long *frame_offset = nullptr)
+{
+    const unsigned halo_transient_bits = halo_flags & 0x3fffffffu;
+    SynthParams p;
+    memset(&p, 0, sizeof p);
+    p.coef = coef;
+    p.transient = transient;
+    p.tail_in = tail_in;
+    p.halo_coef = tail_in ? nullptr : halo_coef;
+    p.halo_transient = (int)halo_transient_bits;
+    p.pcm = pcm;
+    p.tail_out = tail_out;
+    p.tables = ctx->d_fast;
+    p.gen = ctx->d_gen;
+    p.frame_offset = frame_offset;
+    p.halo_lm_shift = (int)(halo_flags >> 30);
+    p.nframes = nframes;
+    int mode = 0;
+    const int rc = plan_layout(L, ctx->num_sms, nframes, &p, &mode);
+    if (rc == NQ_UNIMPLEMENTED)
+        return fail(ctx, rc, "a channel layout needs at most %d warps (coupled streams + pairs of mono streams) and at most 30 streams with their own flags; got %d streams, %d coupled",
+                    kMaxGroupStreams, L.streams, L.coupled);
     NQ_CUDA(ctx, launch_synth(p, mode, ctx->num_sms, stream, nullptr));
     ctx->launches++;
     return NQ_OK;
@@ -337,6 +352,44 @@ void *nq_celt_host_alloc(size_t bytes)
 void nq_celt_host_free(void *p)
 {
     if (p) cudaFreeHost(p);
+}
+
+int nq_celt_debug_plan(int channels, int streams, int coupled_streams, const unsigned char *mapping, int64_t nframes,
+                       int num_sms, int64_t out[12])
+{
+    if (!out || nframes < 0 || num_sms < 1) return NQ_BAD_ARG;
+    Layout L;
+    if (mapping) {
+        const int rc = check_layout(nullptr, channels, streams, coupled_streams, mapping, &L);
+        if (rc != NQ_OK) return rc;
+    } else {
+        if (channels < 1 || channels > 255) return NQ_BAD_ARG;
+        L = plain_layout(channels);
+    }
+    SynthParams p;
+    memset(&p, 0, sizeof p);
+    int mode = 0;
+    const int rc = plan_layout(L, num_sms, nframes, &p, &mode);
+    if (rc != NQ_OK) return rc;
+    bool paired = false;
+    for (int s = 0; s < p.nstreams; s++) paired = paired || p.streams[s].flag_col1 != p.streams[s].flag_col;
+    std::vector<PostJob> jobs;
+    build_post_jobs(L, 0, 0, (int)(nframes > 0x7fffffff ? 0x7fffffff : nframes), false, &jobs);
+    int jobs2 = 0;
+    for (const PostJob &j : jobs) jobs2 += j.nch == 2;
+    out[0] = mode;
+    out[1] = mode == kModeGroup ? p.nstreams : 0;                   // warps per group
+    out[2] = mode == kModeGroup ? groups_per_cta(p.nstreams) : 0;   // groups per CTA
+    out[3] = mode == kModeGroup ? p.store_threads : 0;
+    out[4] = mode == kModeGroup ? p.store_shape : 0;
+    out[5] = paired ? 1 : 0;
+    out[6] = p.frames_per_run;
+    out[7] = p.nruns;
+    out[8] = (int64_t)jobs.size();                                  // post-stage CTAs
+    out[9] = jobs2;                                                 // ... of which two-channel
+    out[10] = L.D;
+    out[11] = L.identity ? 1 : 0;
+    return NQ_OK;
 }
 
 void nq_celt_debug_tables(float *t_long, float *t_short, float *window, float *trig)

@@ -778,9 +778,11 @@ int group_store_threads(int C, int nstreams)
     return 2 * T2 >= T ? T2 : 0;
 }
 
-int synth_mode(int D, int C, int nstreams, bool identity_map)
+// one_decoder: a single CELT decoder (1 or 2 channels sharing one transient flag).  Two mono
+// STREAMS routed to two output channels also have D = C = 2, but each switches blocks on its own.
+int synth_mode(int D, int C, int nstreams, bool identity_map, bool one_decoder)
 {
-    if (D == 2 && C == 2 && nstreams == 1 && identity_map) return kModeStereo;
+    if (D == 2 && C == 2 && nstreams == 1 && identity_map && one_decoder) return kModeStereo;
     if (D == 1 && C == 1 && identity_map) return kModeMono;
     if (nstreams <= kMaxGroupStreams && group_store_threads(C, nstreams) > 0) return kModeGroup;
     return kModeDirect;

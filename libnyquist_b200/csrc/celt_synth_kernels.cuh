@@ -135,7 +135,7 @@ cudaError_t prepare_post_kernel();
 cudaError_t launch_post(const PostParams &p, int njobs, cudaStream_t stream);
 
 size_t fast_kernel_smem_bytes();
-int synth_mode(int D, int C, int nstreams, bool identity_map);
+int synth_mode(int D, int C, int nstreams, bool identity_map, bool one_decoder);
 int groups_per_cta(int nstreams);
 int group_store_threads(int C, int nstreams);
 cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream_t stream, int *launched_ctas);

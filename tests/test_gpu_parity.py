@@ -187,6 +187,7 @@ MS_LAYOUTS = {
     "surround_7.1": (5, 3, [0, 6, 1, 2, 3, 4, 5, 7]),
     "dual_mono_muted_dup": (3, 1, [2, 255, 0, 0, 1, 3, 3]),
     "fourteen_mono": (14, 0, list(range(14))),
+    "dual_mono_identity": (2, 0, [0, 1]),      # D = C = 2 like stereo, but two decoders with their own flags
     "five_mono_odd": (5, 0, [4, 3, 2, 1, 0]),
     "max_warps_13_coupled_2_mono": (15, 13, list(range(28))),
 }

@@ -121,3 +121,50 @@ def test_sharded_synthesis_equals_unsharded_oracle():
             parts.append(pcm)
         got = np.concatenate(parts)
         assert np.array_equal(got, want) and np.array_equal(tail, want_tail)
+
+
+# ---- launch planning per channel layout (pure host code behind nq_celt_debug_plan) -------------
+def test_plan_plain_layouts():
+    st = nq.debug_plan(2)
+    assert st["mode"] == nq.MODE_STEREO and st["post_ctas"] == 1 and st["post_ctas_two_channel"] == 1
+    # one run per resident warp: 148 SMs x 14 warps
+    assert 148 * 14 - 2 <= st["runs"] <= 148 * 14 and st["frames_per_run"] * st["runs"] >= 1_000_000
+    mono = nq.debug_plan(1)
+    assert mono["mode"] == nq.MODE_MONO and mono["post_ctas_two_channel"] == 0
+    c8 = nq.debug_plan(8)
+    assert (c8["mode"], c8["warps_per_group"], c8["groups_per_cta"]) == (nq.MODE_GROUP, 4, 3)
+    assert c8["store_threads"] == 128 and c8["store_shape"] == 0 and not c8["paired_mono"]
+    assert 148 * 3 - 2 <= c8["runs"] <= 148 * 3 and c8["post_ctas"] == 4
+    c3 = nq.debug_plan(3)
+    assert (c3["warps_per_group"], c3["groups_per_cta"]) == (2, 6)
+    assert c3["store_threads"] == 63 and c3["store_shape"] == 1      # 4*T2 must be a multiple of C = 3
+    c6 = nq.debug_plan(6)
+    assert c6["store_threads"] == 96 and c6["store_shape"] == 1      # rows of 6 floats: float4s straddle pairs
+    # tiny batches: runs never shorter than 8 frames
+    small = nq.debug_plan(2, nframes=100)
+    assert small["frames_per_run"] == 8 and small["runs"] == 13
+
+
+def test_plan_multistream_layouts():
+    s71 = nq.debug_plan(8, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7])
+    # 3 coupled streams + the 2 mono streams sharing one warp = 4 warps, 3 groups per 12-warp CTA
+    assert (s71["mode"], s71["warps_per_group"], s71["groups_per_cta"], s71["paired_mono"]) == (nq.MODE_GROUP, 4, 3, 1)
+    assert s71["decoded_channels"] == 8 and s71["store_shape"] == 1 and not s71["identity"]
+    # post stage: (0) (6) (1) (2,3) (4,5) (7): the mapping separates L and R of stream 0
+    assert s71["post_ctas"] == 6 and s71["post_ctas_two_channel"] == 2
+    s51 = nq.debug_plan(6, 4, 2, [0, 4, 1, 2, 3, 5])
+    assert (s51["warps_per_group"], s51["groups_per_cta"], s51["paired_mono"]) == (3, 4, 1)
+    muted = nq.debug_plan(7, 3, 1, [2, 255, 0, 0, 1, 3, 3])
+    assert muted["store_shape"] == 2 and muted["post_ctas"] == 5      # the silent channel gets no post CTA
+    ident = nq.debug_plan(2, 1, 1, [0, 1])
+    assert ident["mode"] == nq.MODE_STEREO and ident["identity"]
+    dual = nq.debug_plan(2, 2, 0, [0, 1])
+    assert (dual["mode"], dual["warps_per_group"], dual["paired_mono"]) == (nq.MODE_GROUP, 1, 1)
+    seven = nq.debug_plan(14, 7, 7, list(range(14)))
+    assert (seven["warps_per_group"], seven["groups_per_cta"]) == (7, 2)   # the 14-warp variant
+    with pytest.raises(nq.NqError) as e:
+        nq.debug_plan(29, 29, 0, list(range(29)))                      # 15 warps: one more than a CTA has
+    assert e.value.code == -5
+    with pytest.raises(nq.NqError) as e:
+        nq.debug_plan(3, 2, 1, [0, 1, 3])                               # decoded channel 3 does not exist
+    assert e.value.code == -1
