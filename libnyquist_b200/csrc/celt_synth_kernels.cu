@@ -93,7 +93,17 @@ static_assert((kInRowFloats * 4) % 16 == 0, "TMA destination rows must be 16-byt
 constexpr int kWarpSmemFloats = int(sizeof(WarpSmem) / 4);
 constexpr int kPlaneOffFloats = 2 * kInRowFloats;   // offsetof(WarpSmem, x) / 4
 
+// This file is compiled four times (-DNQ_PART=0..3, libnyquist_b200/build.py) so the kernel
+// instantiations build in parallel: part 0 = stereo + mono variants, the generic kernel and the
+// host-side dispatch; part 1 = group variants; part 2 = group variants with paired mono streams;
+// part 3 = direct variants.
+#ifndef NQ_PART
+#define NQ_PART 0
+#endif
+
+#if NQ_PART == 0
 size_t fast_kernel_smem_bytes() { return sizeof(FastTables) + kWarpsPerCta * sizeof(WarpSmem); }
+#endif
 
 // Group mode: the warps of one group (one per stream) and their cooperative store pass.
 // The output frame [960][C] is written as 240*C float4; thread tg of the first T2 threads
@@ -477,7 +487,7 @@ __device__ __forceinline__ void short_frame(const SynthParams &p, const FastTabl
 // as 30 x R (30-point codelet, then an R-term direct sum) -- the same arithmetic as
 // mdct_backward_generic_kernel below -- and leaves the frame as a [N][2] plane at the start of
 // ws.x.  What matters is that such frames can sit anywhere inside a batch and hand their tail on.
-__device__ __noinline__ void small_frame_planes(const GenericTables *gt, const float *win, float *in_rows, float2 *xbuf,
+static __device__ __noinline__ void small_frame_planes(const GenericTables *gt, const float *win, float *in_rows, float2 *xbuf,
                                                 float *tails, int lane, int nch, int sh, int trmask)
 {
     const int Nf = kFrame >> sh;
@@ -759,6 +769,60 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
     // (a pending group barrier needs no partner at exit: nobody overwrites a plane any more)
 }
 
+template <int kMode, int kWarps>
+static cudaError_t prepare_variant(int smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(celt_synth_kernel<kMode, kWarps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(celt_synth_kernel<kMode, kWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+template <int kMode, int kWarps>
+static void launch_variant(const SynthParams &p, unsigned grid, size_t smem, cudaStream_t stream)
+{
+    if (p.frame_offset) celt_synth_kernel<kMode, kWarps, true><<<grid, kWarps * 32, smem, stream>>>(p);
+    else celt_synth_kernel<kMode, kWarps, false><<<grid, kWarps * 32, smem, stream>>>(p);
+}
+
+// prepare / launch of the variants each part owns (warps = 12 or 14 for the group parts)
+cudaError_t prepare_part1(int smem);
+cudaError_t prepare_part2(int smem);
+cudaError_t prepare_part3(int smem);
+void launch_part1(const SynthParams &p, int warps, unsigned grid, size_t smem, cudaStream_t stream);
+void launch_part2(const SynthParams &p, int warps, unsigned grid, size_t smem, cudaStream_t stream);
+void launch_part3(const SynthParams &p, int warps, unsigned grid, size_t smem, cudaStream_t stream);
+
+#if NQ_PART == 1
+cudaError_t prepare_part1(int smem)
+{
+    cudaError_t e = prepare_variant<kModeGroup, kWarpsPerCta>(smem);
+    return e != cudaSuccess ? e : prepare_variant<kModeGroup, 12>(smem);
+}
+void launch_part1(const SynthParams &p, int warps, unsigned grid, size_t smem, cudaStream_t stream)
+{
+    if (warps == 12) launch_variant<kModeGroup, 12>(p, grid, smem, stream);
+    else launch_variant<kModeGroup, kWarpsPerCta>(p, grid, smem, stream);
+}
+#elif NQ_PART == 2
+cudaError_t prepare_part2(int smem)
+{
+    cudaError_t e = prepare_variant<kModeGroupPaired, kWarpsPerCta>(smem);
+    return e != cudaSuccess ? e : prepare_variant<kModeGroupPaired, 12>(smem);
+}
+void launch_part2(const SynthParams &p, int warps, unsigned grid, size_t smem, cudaStream_t stream)
+{
+    if (warps == 12) launch_variant<kModeGroupPaired, 12>(p, grid, smem, stream);
+    else launch_variant<kModeGroupPaired, kWarpsPerCta>(p, grid, smem, stream);
+}
+#elif NQ_PART == 3
+cudaError_t prepare_part3(int smem) { return prepare_variant<kModeDirect, kWarpsPerCta>(smem); }
+void launch_part3(const SynthParams &p, int, unsigned grid, size_t smem, cudaStream_t stream)
+{
+    launch_variant<kModeDirect, kWarpsPerCta>(p, grid, smem, stream);
+}
+#endif
+
+#if NQ_PART == 0
 // Warps per CTA of the group variant for this group width (see celt_synth_kernel): 12 unless only
 // 14 fits the group at all or doubles the groups of the CTA (7, 13 or 14 streams).
 static int group_cta_warps(int nstreams) { return nstreams == 7 || nstreams > 12 ? kWarpsPerCta : 12; }
@@ -788,32 +852,15 @@ int synth_mode(int D, int C, int nstreams, bool identity_map, bool one_decoder)
     return kModeDirect;
 }
 
-template <int kMode, int kWarps>
-static cudaError_t prepare_variant(int smem)
-{
-    cudaError_t e = cudaFuncSetAttribute(celt_synth_kernel<kMode, kWarps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(celt_synth_kernel<kMode, kWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-}
-
 cudaError_t prepare_kernels()
 {
     const int smem = (int)fast_kernel_smem_bytes();
     cudaError_t e = prepare_variant<kModeStereo, kWarpsPerCta>(smem);
-    if (e == cudaSuccess) e = prepare_variant<kModeGroup, kWarpsPerCta>(smem);
-    if (e == cudaSuccess) e = prepare_variant<kModeGroup, 12>(smem);
-    if (e == cudaSuccess) e = prepare_variant<kModeGroupPaired, kWarpsPerCta>(smem);
-    if (e == cudaSuccess) e = prepare_variant<kModeGroupPaired, 12>(smem);
-    if (e == cudaSuccess) e = prepare_variant<kModeDirect, kWarpsPerCta>(smem);
     if (e == cudaSuccess) e = prepare_variant<kModeMono, kWarpsPerCta>(smem);
+    if (e == cudaSuccess) e = prepare_part1(smem);
+    if (e == cudaSuccess) e = prepare_part2(smem);
+    if (e == cudaSuccess) e = prepare_part3(smem);
     return e;
-}
-
-template <int kMode, int kWarps>
-static void launch_variant(const SynthParams &p, unsigned grid, size_t smem, cudaStream_t stream)
-{
-    if (p.frame_offset) celt_synth_kernel<kMode, kWarps, true><<<grid, kWarps * 32, smem, stream>>>(p);
-    else celt_synth_kernel<kMode, kWarps, false><<<grid, kWarps * 32, smem, stream>>>(p);
 }
 
 cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream_t stream, int *launched_ctas)
@@ -835,11 +882,9 @@ cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream
     const unsigned grid = (unsigned)ctas;
     if (mode == kModeStereo) launch_variant<kModeStereo, kWarpsPerCta>(p, grid, smem, stream);
     else if (mode == kModeMono) launch_variant<kModeMono, kWarpsPerCta>(p, grid, smem, stream);
-    else if (mode == kModeGroup && paired && warps == 12) launch_variant<kModeGroupPaired, 12>(p, grid, smem, stream);
-    else if (mode == kModeGroup && paired) launch_variant<kModeGroupPaired, kWarpsPerCta>(p, grid, smem, stream);
-    else if (mode == kModeGroup && warps == 12) launch_variant<kModeGroup, 12>(p, grid, smem, stream);
-    else if (mode == kModeGroup) launch_variant<kModeGroup, kWarpsPerCta>(p, grid, smem, stream);
-    else launch_variant<kModeDirect, kWarpsPerCta>(p, grid, smem, stream);
+    else if (mode == kModeGroup && paired) launch_part2(p, warps, grid, smem, stream);
+    else if (mode == kModeGroup) launch_part1(p, warps, grid, smem, stream);
+    else launch_part3(p, warps, grid, smem, stream);
     return cudaGetLastError();
 }
 
@@ -942,5 +987,7 @@ cudaError_t launch_mdct_generic(const MdctCall *d_calls, int ncalls, const Gener
     mdct_backward_generic_kernel<<<ncalls, kGenericThreads, 0, stream>>>(d_calls, d_tables);
     return cudaGetLastError();
 }
+
+#endif   // NQ_PART == 0
 
 }  // namespace nq
