@@ -126,7 +126,10 @@ NQ_API int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const u
  *              frame; needed when the batch holds frames shorter than 20 ms
  *              (SURVEY.md 8(f) row 4).  A flag byte then carries the frame
  *              size too: bit 0 = transient, bits 1-2 = 3 - LM (0 = 20 ms, so
- *              plain 0/1 flags keep meaning 20 ms frames).  Such a frame has
+ *              plain 0/1 flags keep meaning 20 ms frames).  Bit 3 (any batch,
+ *              with or without frame_offset): the decoder was reset before
+ *              this frame, i.e. it overlap-adds against a zero tail -- the
+ *              first frame of another file in a batch of many.  Such a frame has
  *              N = 120 << LM coefficients at the start of each 960-float row
  *              (transient: 1 << LM short blocks interleaved, as the reference).
  *              NULL: every frame is a 20 ms frame, frame f starts at 960 f.
@@ -169,6 +172,18 @@ NQ_API int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt
                                      const float *hist_in, const float *mem_in, float *hist_out, float *mem_out,
                                      int64_t nframes, int channels, int streams, int coupled_streams,
                                      const unsigned char *mapping, void *stream);
+
+/* A batch of MANY independent streams (files): segment k = frames
+ * [seg_start[k], seg_start[k+1]) (HOST array of nseg+1 entries, 0 .. nframes),
+ * every segment filtered from a reset decoder by its own CTA(s) -- the way the
+ * post stage, whose filters are recurrences along time, fills the GPU.  The
+ * synthesis side of such a batch is the ordinary nq_celt_synth_batch_device*
+ * call with flag bit 3 (value 8, "decoder reset before this frame",
+ * celt_decoder_clean.c:846-859) set on the first frame of every segment. */
+NQ_API int nq_celt_post_segments_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *frames,
+                                        const int64_t *seg_start, int nseg, int64_t nframes, int channels,
+                                        int streams, int coupled_streams, const unsigned char *mapping,
+                                        void *stream);
 
 /* Whole phase 2 on host buffers: coefficients + side info in, float PCM out
  * (synthesis, channel mapping, post-filter, de-emphasis), chunks pipelined
@@ -225,7 +240,9 @@ NQ_API int nq_celt_sink_finish(nq_celt_sink *sink, int64_t *decoded_samples);
 /* Pinned blocks of destroyed sinks are recycled process-wide (page-locking is
  * slow); this releases them. */
 NQ_API void nq_celt_sink_trim_pool(void);
-/* OPUS_RESET_STATE (celt_decoder_clean.c:846-859): forget tail, history, memory. */
+/* OPUS_RESET_STATE (celt_decoder_clean.c:846-859): the next frame pushed for every
+ * stream starts from a cleared decoder (tail, history, memory), wherever that
+ * falls relative to the flushes. */
 NQ_API void nq_celt_sink_reset(nq_celt_sink *sink);
 
 /* Same as _host, frames sharded contiguously over `ndev` devices (devices[i]

@@ -40,7 +40,7 @@ EXPORTED_SYMBOLS = [
     "nq_celt_ctx_create", "nq_celt_ctx_destroy", "nq_celt_strerror", "nq_celt_last_error",
     "nq_celt_device_count", "nq_celt_launch_count", "nq_celt_host_alloc", "nq_celt_host_free",
     "nq_celt_synth_batch_device", "nq_celt_synth_batch_device_ms", "nq_celt_synth_batch_host",
-    "nq_celt_synth_batch_host_multi", "nq_celt_post_batch_device", "nq_celt_decode_batch_host",
+    "nq_celt_synth_batch_host_multi", "nq_celt_post_batch_device", "nq_celt_post_segments_device", "nq_celt_decode_batch_host",
     "nq_celt_sink_create", "nq_celt_sink_destroy", "nq_celt_sink_last_error", "nq_celt_sink_push",
     "nq_celt_sink_pending_frames", "nq_celt_sink_pending_samples", "nq_celt_sink_flush", "nq_celt_sink_reset",
     "nq_celt_sink_flush_pinned", "nq_celt_sink_trim_pool", "nq_celt_sink_attach", "nq_celt_sink_finish",
@@ -86,6 +86,7 @@ def load_library():
     L.nq_celt_synth_batch_device_ms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int,
                                                 C.c_int, vp, vp]
     L.nq_celt_post_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.nq_celt_post_segments_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]
     L.nq_celt_decode_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int,
                                             C.c_int, vp]
     L.nq_celt_sink_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp]
@@ -354,6 +355,24 @@ class CeltSynth:
             self._h, ptr(pcm), _vp(fr), ptr(hist_in), ptr(mem_in), ptr(hist), ptr(mem), fr.shape[0], ch,
             int(streams), int(coupled_streams), _vp(mp), C.c_void_p(st)))
         return hist, mem
+
+    def post_segments_torch(self, pcm, frames, seg_start, streams=1, coupled_streams=None, mapping=None, stream=None):
+        """Post stage over a batch of independent segments (files): seg_start = nseg+1 frame indices;
+        every segment starts from a reset decoder and gets its own CTA(s).  In place on pcm."""
+        import torch
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous() and pcm.dim() == 2
+        ch = pcm.shape[1]
+        fr = np.ascontiguousarray(frames, POST_FRAME_DTYPE).reshape(-1, streams)
+        if coupled_streams is None:
+            coupled_streams = 1 if (mapping is None and ch == 2) else 0
+        ss = np.ascontiguousarray(seg_start, np.int64)
+        mp = None if mapping is None else np.ascontiguousarray(mapping, np.uint8)
+        st = (stream if stream is not None else torch.cuda.current_stream(pcm.device)).cuda_stream
+        if st == 0:
+            st = 1
+        self._check(self._L.nq_celt_post_segments_device(self._h, C.c_void_p(pcm.data_ptr()), _vp(fr), _vp(ss), ss.size - 1,
+                                                         fr.shape[0], ch, int(streams), int(coupled_streams), _vp(mp),
+                                                         C.c_void_p(st)))
 
     # -- whole phase 2 on host buffers ----------------------------------------------------------
     def decode_batch(self, coef, transient, frames, state=None, streams=1, coupled_streams=None, mapping=None):

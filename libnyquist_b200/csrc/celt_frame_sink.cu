@@ -145,6 +145,7 @@ struct nq_celt_sink {
     std::deque<Block> blocks;        // blocks[k] holds frames [(first_block + k) * 2048, ...)
     long long first_block = 0;       // blocks already handed to the worker (streaming mode)
     std::vector<long long> pushed;   // frames pushed per stream since the last flush / attach
+    std::vector<char> reset_next;    // the stream's next frame follows a decoder reset (flag bit 3)
     // decoder state between phase-2 calls (have_state == false: reset decoder)
     std::vector<float> tail, hist, mem;
     bool have_state = false;
@@ -295,6 +296,7 @@ int nq_celt_sink_create(nq_celt_sink **out, int channels, int streams, int coupl
     s->D = streams + coupled_streams;
     memcpy(s->mapping, mapping, channels);
     s->pushed.assign(streams, 0);
+    s->reset_next.assign(streams, 0);
     s->tail.assign((size_t)s->D * NQ_CELT_HALF_OVERLAP, 0.f);
     s->hist.assign((size_t)s->D * NQ_CELT_POST_HISTORY, 0.f);
     s->mem.assign(s->D, 0.f);
@@ -344,7 +346,8 @@ int nq_celt_sink_push(nq_celt_sink *s, int stream, const float *freq, int CC, in
     for (int c = 0; c < nch; c++)   // rows keep the 960-float stride whatever the frame size
         memcpy(b.coef + (fi * s->D + row + c) * kFrame, freq + (size_t)c * N, sizeof(float) * N);
     // a frame with one short block IS a long block of the same size (celt_decoder_clean.c:273-284)
-    b.flags[fi * s->streams + stream] = (uint8_t)((shortBlocks > 1 ? 1 : 0) | ((3 - LM) << 1));
+    b.flags[fi * s->streams + stream] = (uint8_t)((shortBlocks > 1 ? 1 : 0) | ((3 - LM) << 1) | (s->reset_next[stream] ? 8 : 0));
+    s->reset_next[stream] = 0;
     b.post[fi * s->streams + stream] = *post;
     s->pushed[stream] = f + 1;
     // streaming: hand every complete block to the worker
@@ -384,11 +387,10 @@ int64_t nq_celt_sink_pending_samples(const nq_celt_sink *s)
 void nq_celt_sink_reset(nq_celt_sink *s)
 {
     if (!s) return;
-    // OPUS_RESET_STATE, celt_decoder_clean.c:846-859: decode_mem, preemph_memD cleared
-    std::fill(s->tail.begin(), s->tail.end(), 0.f);
-    std::fill(s->hist.begin(), s->hist.end(), 0.f);
-    std::fill(s->mem.begin(), s->mem.end(), 0.f);
-    s->have_state = false;
+    // OPUS_RESET_STATE, celt_decoder_clean.c:846-859: decode_mem, preemph_memD cleared.  Frames
+    // already pushed keep their state; the NEXT frame of every stream carries the reset flag, so a
+    // reset may fall anywhere between two pushes (phase 2 zeroes tail / history / memory there).
+    std::fill(s->reset_next.begin(), s->reset_next.end(), 1);
 }
 
 int nq_celt_sink_flush(nq_celt_sink *s, nq_celt_ctx *ctx, float *pcm_out, int64_t capacity_samples, int64_t *nsamples)

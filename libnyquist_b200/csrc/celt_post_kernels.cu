@@ -308,9 +308,9 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
 #pragma unroll
     for (int ch = 0; ch < NCH; ch++) {
         const int row = job.state_row + ch;
-        if (p.hist_out)
+        if (p.hist_out && job.write_state)
             for (int i = tid; i < kPostHist; i += kPostThreads) p.hist_out[(size_t)row * kPostHist + i] = sm.buf[ch][i];
-        if (p.mem_out && tid == 0) p.mem_out[row] = sm.mem[ch];
+        if (p.mem_out && job.write_state && tid == 0) p.mem_out[row] = sm.mem[ch];
     }
 }
 

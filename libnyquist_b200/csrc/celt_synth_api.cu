@@ -179,7 +179,8 @@ Layout plain_layout(int C)
     return L;
 }
 
-void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes, bool reset, std::vector<PostJob> *jobs);
+void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes, bool reset, bool write_state,
+                     std::vector<PostJob> *jobs);
 
 // Everything about a launch that follows from the channel layout and the batch size alone: kernel
 // variant, warps per group, the streams each warp synthesises, the store pass, the runs.  Pure host
@@ -374,7 +375,7 @@ int nq_celt_debug_plan(int channels, int streams, int coupled_streams, const uns
     bool paired = false;
     for (int s = 0; s < p.nstreams; s++) paired = paired || p.streams[s].flag_col1 != p.streams[s].flag_col;
     std::vector<PostJob> jobs;
-    build_post_jobs(L, 0, 0, (int)(nframes > 0x7fffffff ? 0x7fffffff : nframes), false, &jobs);
+    build_post_jobs(L, 0, 0, (int)(nframes > 0x7fffffff ? 0x7fffffff : nframes), false, true, &jobs);
     int jobs2 = 0;
     for (const PostJob &j : jobs) jobs2 += j.nch == 2;
     out[0] = mode;
@@ -539,7 +540,8 @@ static_assert(sizeof(PostFrame) == sizeof(nq_celt_post_frame), "side-info record
 
 // Post jobs of one contiguous frame range: adjacent output channels fed by the two channels of
 // one coupled stream share a warp; every other live channel gets its own; silent channels none.
-void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes, bool reset, std::vector<PostJob> *jobs)
+void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes, bool reset, bool write_state,
+                     std::vector<PostJob> *jobs)
 {
     for (int c = 0; c < L.C;) {
         const int d = L.mapping[c];
@@ -552,6 +554,7 @@ void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes
         j.ch0 = c;
         j.state_row = d;
         j.reset = reset ? 1 : 0;
+        j.write_state = write_state ? 1 : 0;
         if (d < 2 * L.coupled && (d & 1) == 0 && c + 1 < L.C && L.mapping[c + 1] == d + 1) {
             j.nch = 2;
             j.stream_col = d >> 1;
@@ -562,6 +565,24 @@ void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes
             c += 1;
         }
         jobs->push_back(j);
+    }
+}
+
+// Post jobs of frames [0, n) of a (chunk of a) batch whose flag bytes `flags` (host, one record of
+// `fcols` bytes per frame, column 0 examined) may carry kFlagReset: every reset starts a new piece
+// with its own CTAs and a zeroed filter state; the first piece continues from the incoming state
+// unless it opens on a reset; only the last piece leaves its state behind.
+void build_post_jobs_with_resets(const Layout &L, const uint8_t *flags, int fcols, const nq_celt_post_frame *frames,
+                                 long long n, std::vector<PostJob> *jobs)
+{
+    long long start = 0, sample0 = 0, pos = 0;
+    for (long long f = 1; f <= n; f++) {
+        pos += frames[(f - 1) * L.streams].N;
+        if (f == n || (flags[f * fcols] & kFlagReset)) {
+            build_post_jobs(L, sample0, (int)start, (int)(f - start), (flags[start * fcols] & kFlagReset) != 0, f == n, jobs);
+            start = f;
+            sample0 = pos;
+        }
     }
 }
 
@@ -731,7 +752,7 @@ int host_range(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8
         if (rc != NQ_OK) return rc;
         if (pframes) {
             jobs.clear();
-            build_post_jobs(L, 0, 0, (int)n, false, &jobs);
+            build_post_jobs_with_resets(L, transient + f0 * flag_row, (int)flag_row, pframes + f0 * L.streams, n, &jobs);
             if ((int)jobs.size() > ctx->pjobs_cap[s]) {
                 cudaFree(ctx->d_pjobs[s]);
                 ctx->d_pjobs[s] = nullptr;
@@ -789,9 +810,9 @@ int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t 
 }
 
 // ---- post stage + whole phase 2 ------------------------------------------------------------
-int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *frames, const float *hist_in,
-                              const float *mem_in, float *hist_out, float *mem_out, int64_t nframes, int channels,
-                              int streams, int coupled_streams, const unsigned char *mapping, void *stream)
+static int post_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *frames, const int64_t *seg_start, int nseg,
+                       const float *hist_in, const float *mem_in, float *hist_out, float *mem_out, int64_t nframes,
+                       int channels, int streams, int coupled_streams, const unsigned char *mapping, void *stream)
 {
     if (!ctx) return NQ_BAD_ARG;
     Layout L;
@@ -835,7 +856,19 @@ int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_f
     if (rc != NQ_OK) return rc;
     NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pframes_dev, frames, (size_t)nframes * L.streams * sizeof(PostFrame), cudaMemcpyHostToDevice, st));
     std::vector<PostJob> jobs;
-    build_post_jobs(L, 0, 0, (int)nframes, false, &jobs);
+    if (seg_start) {
+        if (nseg < 1 || seg_start[0] != 0 || seg_start[nseg] != nframes) return fail(ctx, NQ_BAD_ARG, "seg_start must run from 0 to nframes");
+        std::vector<long long> first(nframes + 1);
+        first[0] = 0;
+        for (int64_t f = 0; f < nframes; f++) first[f + 1] = first[f] + frames[f * L.streams].N;
+        for (int k = 0; k < nseg; k++) {
+            if (seg_start[k + 1] < seg_start[k]) return fail(ctx, NQ_BAD_ARG, "seg_start must be non-decreasing");
+            if (seg_start[k + 1] > seg_start[k])
+                build_post_jobs(L, first[seg_start[k]], (int)seg_start[k], (int)(seg_start[k + 1] - seg_start[k]), true, false, &jobs);
+        }
+    } else {
+        build_post_jobs(L, 0, 0, (int)nframes, false, true, &jobs);
+    }
     if (jobs.empty()) return NQ_OK;
     if ((int)jobs.size() > ctx->pjobs_dev_cap) {
         cudaFree(ctx->d_pjobs_dev);
@@ -846,6 +879,23 @@ int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_f
     }
     NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pjobs_dev, jobs.data(), jobs.size() * sizeof(PostJob), cudaMemcpyHostToDevice, st));
     return enqueue_post(ctx, L, pcm, ctx->d_pframes_dev, ctx->d_pjobs_dev, (int)jobs.size(), hist_in, mem_in, hist_out, mem_out, st);
+}
+
+int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *frames, const float *hist_in,
+                              const float *mem_in, float *hist_out, float *mem_out, int64_t nframes, int channels,
+                              int streams, int coupled_streams, const unsigned char *mapping, void *stream)
+{
+    return post_device(ctx, pcm, frames, nullptr, 0, hist_in, mem_in, hist_out, mem_out, nframes, channels, streams,
+                       coupled_streams, mapping, stream);
+}
+
+int nq_celt_post_segments_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *frames, const int64_t *seg_start,
+                                 int nseg, int64_t nframes, int channels, int streams, int coupled_streams,
+                                 const unsigned char *mapping, void *stream)
+{
+    if (!seg_start) return NQ_BAD_ARG;
+    return post_device(ctx, pcm, frames, seg_start, nseg, nullptr, nullptr, nullptr, nullptr, nframes, channels, streams,
+                       coupled_streams, mapping, stream);
 }
 
 int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t *transient, const nq_celt_post_frame *frames,
@@ -875,8 +925,8 @@ int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t
     for (int64_t f = 0; f < nframes; f++)
         for (int sidx = 0; sidx < L.streams; sidx++) {
             const int N = frames[f * L.streams + sidx].N, flag = transient[f * fcols + (L.per_stream_flags ? sidx : 0)];
-            if (N != (kFrame >> ((flag >> 1) & 3)) || (flag >> 3))
-                return fail(ctx, NQ_BAD_ARG, "frame %lld stream %d: flag byte 0x%02x does not say N=%d (bit 0 transient, bits 1-2 = 3-LM)",
+            if (N != (kFrame >> ((flag >> 1) & 3)) || (flag >> 4))
+                return fail(ctx, NQ_BAD_ARG, "frame %lld stream %d: flag byte 0x%02x does not say N=%d (bit 0 transient, bits 1-2 = 3-LM, bit 3 reset)",
                             (long long)f, sidx, flag, N);
         }
     HostState st;

@@ -657,7 +657,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         const long long f1 = (f0 + p.frames_per_run < p.nframes) ? f0 + p.frames_per_run : p.nframes;
         // A run that does not open the batch (or a batch with a halo frame)
         // first re-computes the frame before it, only to obtain its raw tail.
-        const bool warm = f0 > 0 || p.halo_coef != nullptr;
+        // ... unless the run opens on a frame that follows a decoder reset (flag bit 3: the first
+        // frame of another file in a batch of many): its tail is zero by definition.
+        const bool warm = (f0 > 0 || p.halo_coef != nullptr) && !(p.transient[f0 * p.flag_stride + flag_col] & kFlagReset);
         for (int i = lane; i < 2 * kHalfOvl; i += 32) {
             const int ch = i / kHalfOvl;
             float t = 0.f;
@@ -695,11 +697,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             const int next_nfr = (kMode == kModeMono && more && mono_pair(f + nfr, next_flag)) ? 2 : 1;
             int next_tr1 = -1;
             if (kPaired && flag_col1 >= 0 && more) next_tr1 = p.transient[(f + 1) * p.flag_stride + flag_col1] & 1;
+            if (flag & kFlagReset) {   // OPUS_RESET_STATE before this frame (celt_decoder_clean.c:846-859)
+                for (int i = lane; i < 2 * kHalfOvl; i += 32) ws.tail[i] = 0.f;
+                __syncwarp();
+            }
             while (!mbar_try_wait(&ws.bar, phase)) {}
             phase ^= 1;
             const bool store = f >= f0;
             const long long off = (kAnySize && store) ? p.frame_offset[f] : f * kFrame;
-            const int sh = kAnySize ? (flag >> 1) & 3 : 0;
+            const int sh = kAnySize ? (flag >> 1) & 3 : 0;   // (bits above 2 are not part of the size)
             int niter = grp.niter;
             const int tr0 = flag & 1;
             const bool split = kPaired && tr1 >= 0 && tr1 != tr0;

@@ -43,6 +43,8 @@ struct GenericTables {
 //   kModeDirect  more streams than a CTA has warps: channel pairs, scattered stores (slow, rare);
 //   kModeMono    D = C = 1: one warp per run like stereo, its two "channels" being two consecutive
 //                frames of the stream whenever they have the same block type.
+// flag byte of a frame: bit 0 transient, bits 1-2 = 3 - LM, bit 3 = the decoder was reset before this frame
+constexpr int kFlagTransient = 1, kFlagReset = 8;
 constexpr int kModeStereo = 0, kModeGroup = 1, kModeDirect = 2;
 constexpr int kModeMono = 4;
 constexpr int kModeGroupPaired = 3;   // kernel-internal: kModeGroup whose warps may carry two independent mono streams
@@ -114,7 +116,7 @@ struct PostJob {
     int stream_col;      // column of the stream inside a frame's side-info record
     int state_row;       // row of channel ch0 in the state arrays (decoded-channel order)
     int reset;           // 1: start from a reset decoder (zero history and memory), ignore *_in
-    int pad_;
+    int write_state;     // 1: leave history / memory in *_out (the piece that ends the batch)
 };
 
 struct PostParams {

@@ -143,6 +143,35 @@ def test_post_multistream_mapping(synth):
     assert not got[:, 6].any()
 
 
+@pytest.mark.parametrize("C", [1, 2])
+def test_batch_of_many_files_reset_flag_and_segments(synth, C):
+    """A batch that concatenates independent streams: flag bit 3 on the first frame of each (the
+    synthesis zeroes its tail there), one post-stage CTA per segment, each from a reset decoder."""
+    import torch
+    from test_gpu_parity import rand_batch
+    rng = np.random.default_rng(50 + C)
+    lens = [700, 1, 2, 1300, 37]
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    nframes = int(seg[-1])
+    coef, tr = rand_batch(rng, nframes, C, 0.1)
+    fr = rand_frames(rng, nframes)
+    flags = tr.copy()
+    flags[seg[:-1]] |= 8
+    want = []
+    for a, b in zip(seg[:-1], seg[1:]):
+        sig, _, _ = port.synth_batch(coef[a:b], tr[a:b], None, nthreads=4)
+        want.append(port.post_batch(sig, fr[a:b])[0])
+    want = np.concatenate(want)
+    d_coef, d_fl = torch.from_numpy(coef).cuda(), torch.from_numpy(flags).cuda()
+    pcm, _ = synth.synth_batch_torch(d_coef, d_fl)
+    synth.post_segments_torch(pcm, fr, seg)
+    torch.cuda.synchronize()
+    assert_pcm(want, pcm.cpu().numpy(), f"segments C {C}")
+    # the host entry reads the same flag bit: one call, same result bit for bit
+    got, _ = synth.decode_batch(coef, flags, fr)
+    assert np.array_equal(got, pcm.cpu().numpy())
+
+
 def test_post_rejects_bad_side_info(synth):
     import torch
     pcm = torch.zeros((960, 2), device="cuda")

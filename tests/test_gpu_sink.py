@@ -52,10 +52,15 @@ def test_sink_flush_equals_decode_batch_and_oracle(synth):
     push_all(sink2, coef[1000:], tr[1000:, None], fr[1000:, None], 1, 1)
     b = sink2.flush(synth)
     assert np.array_equal(np.concatenate([a, b]), got)
-    # ... and reset() forgets it
+    # ... and reset() forgets it, between flushes or in the middle of one
     sink2.reset()
     push_all(sink2, coef[:50], tr[:50, None], fr[:50, None], 1, 1)
     assert np.array_equal(sink2.flush(synth), got[:50 * 960])
+    push_all(sink2, coef[50:90], tr[50:90, None], fr[50:90, None], 1, 1)
+    sink2.reset()
+    push_all(sink2, coef[:30], tr[:30, None], fr[:30, None], 1, 1)
+    mid = sink2.flush(synth)
+    assert np.array_equal(mid[:40 * 960], got[50 * 960:90 * 960]) and np.array_equal(mid[40 * 960:], got[:30 * 960])
 
 
 def test_sink_streaming_equals_flush_with_window(synth):
