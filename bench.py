@@ -226,6 +226,42 @@ def extras(torch, np, nq, synth, dev, peak, with_cpu_baseline):
         del c, t, o
     out["other_layouts_device_resident"] = shapes
 
+    # whole phase 2 (synthesis + post-filter + de-emphasis) over a batch of many independent stereo
+    # streams: the post stage's filters are recurrences along time, so it fills the GPU with streams
+    try:
+        nseg, per = 4096, 256
+        frames = nseg * per
+        c = torch.empty((frames, 2, 960), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g).mul_(1000.0)
+        fl = (torch.rand(frames, generator=g, device=dev) < P_TRANSIENT).to(torch.uint8)
+        fl[::per] |= 8                                   # decoder reset at the head of every stream
+        o = torch.empty((frames * 960, 2), dtype=torch.float32, device=dev)
+        rng = np.random.default_rng(3)
+        fr = np.zeros(frames, nq.POST_FRAME_DTYPE)
+        fr["N"] = 960
+        pitch = rng.integers(15, 1023, frames + 1)
+        gain = (rng.integers(0, 9, frames + 1) * 0.09375).astype(np.float32)
+        tap = rng.integers(0, 3, frames + 1)
+        fr["pitch"] = np.stack([pitch[:-1], pitch[:-1], pitch[1:]], 1)
+        fr["gain"] = np.stack([gain[:-1], gain[:-1], gain[1:]], 1)
+        fr["tapset"] = np.stack([tap[:-1], tap[:-1], tap[1:]], 1)
+        seg = np.arange(nseg + 1, dtype=np.int64) * per
+
+        def phase2():
+            synth.synth_batch_torch(c, fl, out=o, want_tail=False)
+            synth.post_segments_torch(o, fr, seg)
+
+        ms = timed(phase2, steps=3)
+        ms_synth = timed(lambda: synth.synth_batch_torch(c, fl, out=o, want_tail=False), steps=3)
+        gbs = frames * 2 * BYTES_PER_FRAME / (ms * 1e-3) / 1e9
+        out["phase2_many_streams"] = {
+            "what": f"{nseg} independent stereo streams x {per} frames: synthesis kernel + post kernel (one CTA per stream), "
+                    "side info uploaded from pageable host memory inside the call",
+            "frames": frames, "ms": ms, "ms_synthesis_only": ms_synth, "frames_per_s": frames / (ms * 1e-3),
+            "GBps_algorithmic_4_passes": gbs, "frac_of_hbm_peak": gbs / peak}
+        del c, fl, o
+    except Exception as e:   # informational leg: never fail the bench line
+        out["phase2_many_streams_error"] = repr(e)
+
     # PCIe ceiling of the e2e leg: concurrent pinned H2D + D2H copies of 256 MB each
     n = 64 << 20
     h_a = torch.empty(n, dtype=torch.float32, pin_memory=True)

@@ -29,9 +29,14 @@ constexpr int kPostThreads = 128;            // one CTA = one stream (1 or 2 cha
 constexpr int kPostSegs = 120;               // de-emphasis segments: N / 120 = 8, 4, 2, 1 samples each
 constexpr unsigned kFullMask = 0xffffffffu;
 
+constexpr int kOff = 1028;                   // the current frame starts here: 16-byte aligned, history in [2, 1028)
+constexpr int kStagePad = 4;                 // floats of padding after every 8 samples of the staging buffer
+
 struct __align__(16) PostSmem {
-    float buf[2][kPostHist + kFrame + 6];   // per channel: [0, 1026) filtered history, then the current frame
-    float stage[2 * kFrame];                // de-emphasised frame [n][nch]
+    float buf[2][kOff + kFrame + 4];         // per channel: filtered history, then the current frame
+    // de-emphasised frame, 8 samples x nch channels then 4 floats of padding: a thread that owns
+    // 8 consecutive samples reads / writes them as 128-bit words without bank conflicts
+    float stage[(kFrame / 8) * (16 + kStagePad)];
     float win2[kOverlap];                   // window[i]^2, celt.c:147
     float wtot[2][4];                       // de-emphasis: per-warp carries
     float mem[2];                           // de-emphasis state (preemph_memD)
@@ -61,7 +66,7 @@ __device__ __forceinline__ Taps make_taps(int T, float g, int tapset)
     return t;
 }
 
-// One region [a, b) of a frame, in place (frame sample i lives at buf[ch][kPostHist + i]).
+// One region [a, b) of a frame, in place (frame sample i lives at buf[ch][kOff + i]).
 //   xfade: celt.c:142-166, the filter fades from `t0` to `t1` with window^2 over the region
 //   else : celt.c:176 / pitch_sse.h:104, constant filter `t1`
 // Samples inside a block of min(T)-2 are independent of each other; blocks run in order, one
@@ -81,7 +86,7 @@ __device__ __forceinline__ void comb_region(PostSmem &sm, int a, int b, const Ta
             if (xfade) f = sm.win2[i - a];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
-                float *x = sm.buf[ch] + kPostHist + i;
+                float *x = sm.buf[ch] + kOff + i;
                 float acc = x[0];
                 if (use0) {
                     const float *q = x - t0.T;
@@ -108,6 +113,10 @@ __device__ __forceinline__ void comb_region(PostSmem &sm, int a, int b, const Ta
     }
 }
 
+// float offset of sample n (channel 0) in the staging buffer
+template <int NCH>
+__device__ __forceinline__ int stage_at(int n) { return (n >> 3) * (8 * NCH + kStagePad) + (n & 7) * NCH; }
+
 // deemphasis, celt_decoder_clean.c:232-241, over the N filtered samples of the frame: thread
 // t < 120 owns samples [t*seg, (t+1)*seg), seg = N/120; the segment carries (affine maps
 // m -> m_seg + a^seg m) are combined by a warp scan plus a 4-entry hand-over between the warps.
@@ -121,15 +130,29 @@ __device__ __forceinline__ void deemphasis_frame(PostSmem &sm, int N, int tid)
     float A = a;                       // a^seg
     for (int k = 1; k < seg; k <<= 1) A *= A;
     float m[NCH];
+    float v[NCH][8];                   // the thread's segment (20 ms frames: 8 samples per channel, in registers)
+    const bool fast = seg == 8;
 #pragma unroll
     for (int ch = 0; ch < NCH; ch++) {
         m[ch] = tid == 0 ? sm.mem[ch] : 0.f;   // thread 0 starts from the incoming state, the others from 0
         if (act) {
-            const float *x = sm.buf[ch] + kPostHist + tid * seg;
-            for (int j = 0; j < seg; j++) {
-                const float tmp = x[j] + m[ch] + 1e-30f;   // VERY_SMALL, arch.h:195
-                m[ch] = a * tmp;
-                sm.stage[(tid * seg + j) * NCH + ch] = tmp;
+            const float *x = sm.buf[ch] + kOff + tid * seg;
+            if (fast) {
+                const float4 lo = *reinterpret_cast<const float4 *>(x), hi = *reinterpret_cast<const float4 *>(x + 4);
+                v[ch][0] = lo.x; v[ch][1] = lo.y; v[ch][2] = lo.z; v[ch][3] = lo.w;
+                v[ch][4] = hi.x; v[ch][5] = hi.y; v[ch][6] = hi.z; v[ch][7] = hi.w;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float tmp = v[ch][j] + m[ch] + 1e-30f;   // VERY_SMALL, arch.h:195
+                    m[ch] = a * tmp;
+                    v[ch][j] = tmp;
+                }
+            } else {
+                for (int j = 0; j < seg; j++) {
+                    const float tmp = x[j] + m[ch] + 1e-30f;
+                    m[ch] = a * tmp;
+                    sm.stage[stage_at<NCH>(tid * seg + j) + ch] = tmp;
+                }
             }
         }
     }
@@ -158,12 +181,31 @@ __device__ __forceinline__ void deemphasis_frame(PostSmem &sm, int N, int tid)
         const float prev = __shfl_up_sync(kFullMask, m[ch], 1);
         const float cin = lane == 0 ? cw : fmaf(Al, cw, prev);   // state entering this thread's segment
         if (tid == kPostSegs - 1) sm.mem[ch] = fmaf(Al * A, cw, m[ch]);
-        if (act && tid > 0) {
-            float pw = 1.f;   // a^j
+        if (act && fast) {
+            if (tid > 0) {
+                float pw = 1.f;   // a^j
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    v[ch][j] = fmaf(pw, cin, v[ch][j]);
+                    pw *= a;
+                }
+            }
+        } else if (act && tid > 0) {
+            float pw = 1.f;
             for (int j = 0; j < seg; j++) {
-                sm.stage[(tid * seg + j) * NCH + ch] += pw * cin;
+                sm.stage[stage_at<NCH>(tid * seg + j) + ch] += pw * cin;
                 pw *= a;
             }
+        }
+    }
+    if (act && fast) {   // 8 samples x NCH channels, interleaved, as 128-bit words (conflict-free thanks to the padding)
+        float4 *dst = reinterpret_cast<float4 *>(sm.stage + tid * (8 * NCH + kStagePad));
+        if (NCH == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) dst[j >> 1] = make_float4(v[0][j], v[NCH - 1][j], v[0][j + 1], v[NCH - 1][j + 1]);
+        } else {
+            dst[0] = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+            dst[1] = make_float4(v[0][4], v[0][5], v[0][6], v[0][7]);
         }
     }
     __syncthreads();
@@ -178,7 +220,7 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
     for (int ch = 0; ch < NCH; ch++) {
         const int row = job.state_row + ch;
         const float *h = (p.hist_in && !job.reset) ? p.hist_in + (size_t)row * kPostHist : nullptr;
-        for (int i = tid; i < kPostHist; i += kPostThreads) sm.buf[ch][i] = h ? h[i] : 0.f;
+        for (int i = tid; i < kPostHist; i += kPostThreads) sm.buf[ch][kOff - kPostHist + i] = h ? h[i] : 0.f;
         if (tid == 0) sm.mem[ch] = (p.mem_in && !job.reset) ? p.mem_in[row] : 0.f;
     }
     __syncthreads();
@@ -210,33 +252,33 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int i = 2 * (tid + 120 * k);
-                    sm.buf[0][kPostHist + i] = nxt[k].x;
-                    sm.buf[1 % NCH][kPostHist + i] = nxt[k].y;
-                    sm.buf[0][kPostHist + i + 1] = nxt[k].z;
-                    sm.buf[1 % NCH][kPostHist + i + 1] = nxt[k].w;
+                    sm.buf[0][kOff + i] = nxt[k].x;
+                    sm.buf[1 % NCH][kOff + i] = nxt[k].y;
+                    sm.buf[0][kOff + i + 1] = nxt[k].z;
+                    sm.buf[1 % NCH][kOff + i + 1] = nxt[k].w;
                 }
             have_nxt = false;
         } else if (NCH == 2 && C == 2) {
             const float4 *g4 = reinterpret_cast<const float4 *>(g);
             for (int i = tid; i < N / 2; i += kPostThreads) {
                 const float4 v = __ldcs(g4 + i);
-                sm.buf[0][kPostHist + 2 * i] = v.x;
-                sm.buf[1 % NCH][kPostHist + 2 * i] = v.y;
-                sm.buf[0][kPostHist + 2 * i + 1] = v.z;
-                sm.buf[1 % NCH][kPostHist + 2 * i + 1] = v.w;
+                sm.buf[0][kOff + 2 * i] = v.x;
+                sm.buf[1 % NCH][kOff + 2 * i] = v.y;
+                sm.buf[0][kOff + 2 * i + 1] = v.z;
+                sm.buf[1 % NCH][kOff + 2 * i + 1] = v.w;
             }
         } else if (NCH == 2 && ((C | job.ch0) & 1) == 0) {   // 8-byte aligned {ch0, ch0+1} pairs
 #pragma unroll 4
             for (int i = tid; i < N; i += kPostThreads) {
                 const float2 v = __ldcs(reinterpret_cast<const float2 *>(g + (size_t)i * C));
-                sm.buf[0][kPostHist + i] = v.x;
-                sm.buf[1 % NCH][kPostHist + i] = v.y;
+                sm.buf[0][kOff + i] = v.x;
+                sm.buf[1 % NCH][kOff + i] = v.y;
             }
         } else {
 #pragma unroll 4
             for (int i = tid; i < N; i += kPostThreads)
 #pragma unroll
-                for (int ch = 0; ch < NCH; ch++) sm.buf[ch][kPostHist + i] = __ldcs(g + (size_t)i * C + ch);
+                for (int ch = 0; ch < NCH; ch++) sm.buf[ch][kOff + i] = __ldcs(g + (size_t)i * C + ch);
         }
         if (stereo2 && f + 1 < job.nframes && pf_next.N == kFrame) {
             const float4 *g4 = reinterpret_cast<const float4 *>(p.pcm + (s0 + N) * 2);
@@ -265,21 +307,20 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
             const float4 *s4 = reinterpret_cast<const float4 *>(sm.stage);
             float4 *g4 = reinterpret_cast<float4 *>(g);
             for (int i = tid; i < N / 2; i += kPostThreads) {
-                float4 v = s4[i];
+                float4 v = s4[(i >> 2) * ((16 + kStagePad) / 4) + (i & 3)];   // samples 2i, 2i+1 of both channels
                 v.x *= kScale; v.y *= kScale; v.z *= kScale; v.w *= kScale;
                 __stcs(g4 + i, v);
             }
         } else if (NCH == 2 && ((C | job.ch0) & 1) == 0) {
-            const float2 *s2 = reinterpret_cast<const float2 *>(sm.stage);
             for (int i = tid; i < N; i += kPostThreads) {
-                float2 v = s2[i];
+                float2 v = *reinterpret_cast<const float2 *>(sm.stage + stage_at<NCH>(i));
                 v.x *= kScale; v.y *= kScale;
                 __stcs(reinterpret_cast<float2 *>(g + (size_t)i * C), v);
             }
         } else {
             for (int i = tid; i < N; i += kPostThreads)
 #pragma unroll
-                for (int ch = 0; ch < NCH; ch++) __stcs(g + (size_t)i * C + ch, sm.stage[i * NCH + ch] * kScale);
+                for (int ch = 0; ch < NCH; ch++) __stcs(g + (size_t)i * C + ch, sm.stage[stage_at<NCH>(i) + ch] * kScale);
         }
         // slide the history: the last 1026 filtered samples move to the front (celt_decoder_clean.c:622-626)
         {
@@ -290,7 +331,7 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
 #pragma unroll
                 for (int k = 0; k < kPer; k++) {
                     const int i = tid + kPostThreads * k;
-                    keep[ch][k] = i < kPostHist ? sm.buf[ch][N + i] : 0.f;
+                    keep[ch][k] = i < kPostHist ? sm.buf[ch][kOff - kPostHist + N + i] : 0.f;
                 }
             __syncthreads();
 #pragma unroll
@@ -298,7 +339,7 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
 #pragma unroll
                 for (int k = 0; k < kPer; k++) {
                     const int i = tid + kPostThreads * k;
-                    if (i < kPostHist) sm.buf[ch][i] = keep[ch][k];
+                    if (i < kPostHist) sm.buf[ch][kOff - kPostHist + i] = keep[ch][k];
                 }
         }
         __syncthreads();
@@ -309,12 +350,12 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
     for (int ch = 0; ch < NCH; ch++) {
         const int row = job.state_row + ch;
         if (p.hist_out && job.write_state)
-            for (int i = tid; i < kPostHist; i += kPostThreads) p.hist_out[(size_t)row * kPostHist + i] = sm.buf[ch][i];
+            for (int i = tid; i < kPostHist; i += kPostThreads) p.hist_out[(size_t)row * kPostHist + i] = sm.buf[ch][kOff - kPostHist + i];
         if (p.mem_out && job.write_state && tid == 0) p.mem_out[row] = sm.mem[ch];
     }
 }
 
-__global__ void __launch_bounds__(kPostThreads) celt_post_kernel(const __grid_constant__ PostParams p)
+__global__ void __launch_bounds__(kPostThreads, 5) celt_post_kernel(const __grid_constant__ PostParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PostSmem &sm = *reinterpret_cast<PostSmem *>(smem_raw);
