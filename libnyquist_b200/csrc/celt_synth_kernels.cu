@@ -633,8 +633,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         item_stride = (long long)gridDim.x * kWarps;
         nitems = p.nruns * p.npairs;
     }
+    // Dynamic distribution (stereo / mono with a work counter): the first kWarps * gridDim items are
+    // assigned statically, every later one is claimed with an atomic when a warp finishes its run --
+    // SMs do not progress at the same pace (HBM channel contention), and short runs claimed on
+    // demand keep the tail of the launch short.
+    const bool dynamic = kMode != kModeGroup && p.work_counter != nullptr;
     uint32_t phase = 0;
-    for (; item < nitems; item += item_stride) {
+    for (; item < nitems;) {
         long long run;
         int cb, nch, flag_col, halo_bit, flag_col1 = -1;
         if (kMode == kModeGroup) {
@@ -771,6 +776,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             }
         }
         __syncwarp();
+        if (dynamic) {
+            unsigned long long next = 0;
+            if (lane == 0) next = atomicAdd(p.work_counter, 1ULL) + (unsigned long long)item_stride;
+            item = (long long)__shfl_sync(kFull, next, 0);
+        } else {
+            item += item_stride;
+        }
     }
     // (a pending group barrier needs no partner at exit: nobody overwrites a plane any more)
 }

@@ -70,6 +70,7 @@ struct SynthParams {
     const FastTables *tables;
     const GenericTables *gen;          // reference trig table: frames shorter than 20 ms
     const long long *frame_offset;     // [nframes] first sample of every frame, or nullptr: frame f starts at 960 f
+    unsigned long long *work_counter;  // zeroed before the launch: runs beyond the first wave are claimed dynamically; nullptr: static
     long long nframes;
     long long frames_per_run;
     long long nruns;
