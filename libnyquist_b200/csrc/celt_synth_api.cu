@@ -146,9 +146,10 @@ int fail(nq_celt_ctx *ctx, int code, const char *fmt, ...)
 // Every run after the first re-computes one extra frame (its predecessor) to
 // obtain the raw tail, so runs are kept long: >= 8 frames when the batch
 // allows, and otherwise just long enough to give every resident item one run.
-// Stereo runs are kept short and claimed dynamically: measured 383 -> 411 M frames/s at 4 M frames for
+// Runs are kept short and claimed dynamically: stereo measured 383 -> 411 M frames/s at 4 M frames for
 // any run length between 32 and 96 (the warm-up frame of every run costs 1/64 extra coefficient reads).
-// Mono runs start with a single (half-efficient) frame before pairing up, which eats the gain: static.
+// Mono runs start with a single (half-efficient) frame before pairing up: twice as long (+2 %); the
+// issue-bound group variants gain 0-2 %.
 constexpr long long kDynamicRun = 64;
 
 void plan_runs(long long nframes, long long resident_items, long long max_run, long long *frames_per_run, long long *nruns)
@@ -246,10 +247,15 @@ int plan_layout(const Layout &L, int num_sms, long long nframes, SynthParams *pp
     }
     // stereo / mono: short runs claimed dynamically (see celt_synth_kernel); the warm-up frame of every
     // run costs 1/kDynamicRun extra coefficient reads
-    long long max_run = mode == kModeStereo ? kDynamicRun : 0;
+    long long max_run = mode == kModeMono ? 2 * kDynamicRun : (mode == kModeDirect ? 0 : kDynamicRun);
     if (const char *e = getenv("NQ_FRAMES_PER_RUN")) max_run = atoll(e);   // tuning knob (0 = one run per resident warp)
     plan_runs(nframes, resident, max_run, &p.frames_per_run, &p.nruns);
     return NQ_OK;
+}
+
+long long resident_items(const SynthParams &p, int mode, int num_sms)
+{
+    return mode == kModeGroup ? (long long)num_sms * groups_per_cta(p.nstreams) : (long long)num_sms * kWarpsPerCta / p.npairs;
 }
 
 // halo_flags: bit s = transient flag of stream s of the halo frame (bit 0 for everybody without
@@ -278,7 +284,7 @@ int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const ui
     if (rc == NQ_UNIMPLEMENTED)
         return fail(ctx, rc, "a channel layout needs at most %d warps (coupled streams + pairs of mono streams) and at most 30 streams with their own flags; got %d streams, %d coupled",
                     kMaxGroupStreams, L.streams, L.coupled);
-    if ((mode == kModeStereo || mode == kModeMono) && p.nruns > (long long)ctx->num_sms * kWarpsPerCta) {
+    if (p.nruns > resident_items(p, mode, ctx->num_sms)) {
         // one counter per launch in flight (launches on different streams may overlap)
         p.work_counter = ctx->d_work + (ctx->work_slot++ % nq_celt_ctx::kWorkSlots);
         NQ_CUDA(ctx, cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), stream));

@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
     // assigned statically, every later one is claimed with an atomic when a warp finishes its run --
     // SMs do not progress at the same pace (HBM channel contention), and short runs claimed on
     // demand keep the tail of the launch short.
-    const bool dynamic = kMode != kModeGroup && p.work_counter != nullptr;
+    const bool dynamic = p.work_counter != nullptr;
     uint32_t phase = 0;
     for (; item < nitems;) {
         long long run;
@@ -776,7 +776,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             }
         }
         __syncwarp();
-        if (dynamic) {
+        if (dynamic && kMode == kModeGroup) {   // the group's first warp claims, the others read it after a group barrier
+            unsigned long long *slot0 = &wsmem[warp - slot].pad_;
+            if (slot == 0 && lane == 0) *slot0 = atomicAdd(p.work_counter, 1ULL) + (unsigned long long)item_stride;
+            group_sync(grp);
+            item = (long long)*slot0;
+        } else if (dynamic) {
             unsigned long long next = 0;
             if (lane == 0) next = atomicAdd(p.work_counter, 1ULL) + (unsigned long long)item_stride;
             item = (long long)__shfl_sync(kFull, next, 0);
