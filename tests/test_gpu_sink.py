@@ -118,3 +118,39 @@ def test_sink_rejects_inconsistent_pushes(synth):
     sink.push(0, np.zeros((2, 960), np.float32), 0, fr)
     with pytest.raises(nq.NqError):
         sink.flush(synth)                                       # stream 1 has not pushed its frame
+
+
+def test_sink_5_1_mixed_frame_sizes_streaming(synth):
+    """Everything at once: 5.1 multistream (2 coupled + 2 mono streams sharing a warp), frames of
+    2.5 / 5 / 10 / 20 ms, per-stream block switching, post-filter, streaming phase 2, pre-skip window."""
+    from test_gpu_parity import oracle_any_size
+    streams, coupled, mapping = MS_LAYOUTS["surround_5.1"]
+    D = streams + coupled
+    rng = np.random.default_rng(5)
+    nframes = 2300
+    lm = rng.choice([3, 3, 3, 2, 1, 0], nframes)
+    coef, _ = rand_batch(rng, nframes, D, 0.0)
+    tr = (rng.uniform(size=(nframes, streams)) < 0.15).astype(np.uint8)
+    fr = np.stack([rand_frames(rng, nframes) for _ in range(streams)], axis=1)
+    fr["N"] = (120 << lm)[:, None]
+    sink = nq.FrameSink(len(mapping), streams, coupled, mapping)
+    total = int((120 << lm).sum())
+    skip = 100
+    dst = np.zeros((total - skip, len(mapping)), np.float32)
+    sink.attach(synth, dst, skip)
+    for f in range(nframes):
+        N = 120 << lm[f]
+        for s in range(streams):
+            rows = [2 * s, 2 * s + 1] if s < coupled else [s + coupled]
+            sink.push(s, np.ascontiguousarray(coef[f, rows, :N]), (1 << lm[f]) if tr[f, s] else 0, fr[f, s])
+    assert sink.finish() == total
+    want = np.zeros((total, len(mapping)), np.float32)
+    for s in range(streams):
+        rows = [2 * s, 2 * s + 1] if s < coupled else [s + coupled]
+        flags = (tr[:, s] | ((3 - lm) << 1)).astype(np.uint8)
+        sig, _, _ = oracle_any_size(np.ascontiguousarray(coef[:, rows]), flags, None)
+        pcm, _, _ = port.post_batch(sig, np.ascontiguousarray(fr[:, s]))
+        for c, d in enumerate(mapping):
+            if d in rows:
+                want[:, c] = pcm[:, rows.index(d)]
+    assert_pcm(want[skip:], dst, "5.1 mixed sizes through the sink")

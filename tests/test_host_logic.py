@@ -169,3 +169,47 @@ def test_plan_multistream_layouts():
     with pytest.raises(nq.NqError) as e:
         nq.debug_plan(3, 2, 1, [0, 1, 3])                               # decoded channel 3 does not exist
     assert e.value.code == -1
+
+
+# ---- reference-side integration library (integration/, built where /root/reference exists) -----
+TWOPHASE = os.path.join(ROOT, "integration", "_build", "libnyquist_twophase.so")
+
+
+@pytest.mark.skipif(not os.path.exists(TWOPHASE), reason="integration/_build not built (needs /root/reference)")
+def test_two_phase_library_loads_and_refuses_to_decode_without_a_gpu():
+    """nqr::NyquistIO::Load of the two-phase build has no CPU synthesis to fall back to: without a
+    usable B200 it must fail loudly (exception -> -1 from the shim), never return audio."""
+    import ctypes as C
+    import torch
+    L = C.CDLL(TWOPHASE)
+    for sym in ("nq_twophase_load", "nq_twophase_free", "nq_twophase_last_timing", "nq_phase1_frame_tap", "nq_phase1_note_silk"):
+        assert hasattr(L, sym), sym
+    if torch.cuda.is_available():
+        pytest.skip("this check is about the GPU-less case")
+    path = os.path.join(ROOT, "oracle", "_ref", "test_data", "short.opus")
+    if not os.path.exists(path):
+        pytest.skip("bundled short.opus not staged")
+    L.nq_twophase_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t),
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    p, n, ch, sr = C.POINTER(C.c_float)(), C.c_size_t(0), C.c_int(0), C.c_int(0)
+    assert L.nq_twophase_load(path.encode(), C.byref(p), C.byref(n), C.byref(ch), C.byref(sr), None) == -1
+    assert not p
+
+
+def test_overlay_files_contain_no_reference_code():
+    """The phase-1 overlays are macro redirections + #include_next, nothing else."""
+    for rel in ("integration/overlay/opus/celt/celt_decoder_clean.c", "integration/overlay/opus/libopus/src/opus_decoder_clean.c",
+                "oracle/ref_overlay/opus/celt/celt_decoder_clean.c"):
+        src = open(os.path.join(ROOT, rel)).read()
+        code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        lines = [l.strip() for l in code.splitlines() if l.strip()]
+        joined = []
+        for l in lines:           # glue continuation lines
+            if joined and joined[-1].endswith("\\"):
+                joined[-1] = joined[-1][:-1] + " " + l
+            else:
+                joined.append(l)
+        assert any(l.startswith("#include_next") for l in joined), rel
+        for l in joined:
+            assert l.startswith("#") or l.startswith("void nqref_tap") or l.startswith("int ") or l.startswith("const float") or l.endswith(";"), (rel, l)
+        assert len(joined) < 25, rel
