@@ -46,6 +46,9 @@ def lib():
         L.nqref_record_copy.argtypes = [fp]
         L.nqref_comb_floats.restype = C.c_size_t
         L.nqref_comb_copy.argtypes = [fp]
+        L.nqref_last_layout.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+        L.nqref_encode_surround.argtypes = [fp, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_long]
+        L.nqref_encode_surround.restype = C.c_long
         L.nqref_comb_filter.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
         L.nqref_deemphasis.argtypes = [C.POINTER(fp), fp, C.c_int, C.c_int, fp]
         _lib = L
@@ -144,7 +147,8 @@ def decode_file(path: str, record: bool = False):
             # (celt_decoder_clean.c:663-669); LM follows from the record's frame length.
             ncalls = nch * (1 if nn == 120 else 2)
             calls = comb[cpos:cpos + ncalls]; cpos += ncalls
-            recs.append(dict(nch=int(nch), shift=int(shift), B=int(B), coef=coef, out=out, comb=calls))
+            recs.append(dict(nch=int(nch), shift=int(shift), B=int(B), coef=coef, out=out, comb=calls,
+                             stream=int(calls[0][7])))   # multistream: index of the CELT decoder that produced it
         assert cpos == len(comb), (cpos, len(comb))
     return pcm, recs
 
@@ -153,6 +157,37 @@ def header_info():
     """(pre_skip, output_gain) of the file decoded last (opusfile OpusHead)."""
     L = lib()
     return int(L.nqref_last_pre_skip()), int(L.nqref_last_output_gain())
+
+
+def layout_info():
+    """(channels, streams, coupled_streams, mapping) of the file decoded last (OpusHead)."""
+    st, cp = C.c_int(0), C.c_int(0)
+    mp = np.zeros(256, np.uint8)
+    ch = lib().nqref_last_layout(C.byref(st), C.byref(cp), mp.ctypes.data_as(C.c_void_p))
+    return ch, st.value, cp.value, [int(v) for v in mp[:ch]]
+
+
+def decode_bytes(data: bytes, record: bool = False):
+    """decode_file for an in-memory Ogg Opus file."""
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".opus") as f:
+        f.write(data)
+        f.flush()
+        return decode_file(f.name, record)
+
+
+def encode_surround(pcm: np.ndarray, bitrate: int = 512000) -> bytes:
+    """The reference's own surround ENCODER (opus_multistream_encoder.c:557, CELT-only) + libogg:
+    pcm [nsamples][channels] float32 in [-1, 1], nsamples a multiple of 960 -> an Ogg Opus file."""
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    n, ch = pcm.shape
+    assert n % FRAME == 0
+    cap = 1 << 24
+    out = np.zeros(cap, np.uint8)
+    got = lib().nqref_encode_surround(_fp(pcm), n, ch, int(bitrate), out.ctypes.data_as(C.c_void_p), cap)
+    if got < 0:
+        raise RuntimeError(f"reference encoder failed: {got}")
+    return out[:got].tobytes()
 
 
 def comb_filter(buf: np.ndarray, start: int, T0, T1, N, g0, g1, tapset0, tapset1) -> None:

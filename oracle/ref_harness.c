@@ -234,27 +234,43 @@ void nqref_tap_mdct(const mdct_lookup *l, float *in, float *out,
     if (g_rec.active) rec_group(1, shift, stride, &in, &out);
 }
 
-/* comb_filter tap: one 8-float record per call {N, T0, T1, g0, g1, tapset0, tapset1, 0}. */
-void nqref_tap_comb_filter(float *y, float *x, int T0, int T1, int N, float g0, float g1,
+/* comb_filter tap: one 8-float record per call {N, T0, T1, g0, g1, tapset0, tapset1, stream},
+ * stream = index of the calling CELT decoder in first-seen order, which is the order
+ * opus_multistream_decode_native walks the streams in (opus_multistream_decoder.c:237). */
+static const void *g_decoders[256];
+static int g_ndecoders;
+
+void nqref_tap_comb_filter(const void *decoder, float *y, float *x, int T0, int T1, int N, float g0, float g1,
                            int tapset0, int tapset1, const float *window, int overlap)
 {
     comb_filter(y, x, T0, T1, N, g0, g1, tapset0, tapset1, window, overlap);
     if (g_rec.active) {
         float *r;
+        int sidx = 0;
+        while (sidx < g_ndecoders && g_decoders[sidx] != decoder) sidx++;
+        if (sidx == g_ndecoders && g_ndecoders < 256) g_decoders[g_ndecoders++] = decoder;
         if (g_rec.clen + 8 > g_rec.ccap) {
             g_rec.ccap = g_rec.ccap ? g_rec.ccap * 2 : (1u << 16);
             g_rec.cbuf = (float *)realloc(g_rec.cbuf, g_rec.ccap * sizeof(float));
         }
         r = g_rec.cbuf + g_rec.clen;
         r[0] = (float)N; r[1] = (float)T0; r[2] = (float)T1; r[3] = g0; r[4] = g1;
-        r[5] = (float)tapset0; r[6] = (float)tapset1; r[7] = 0;
+        r[5] = (float)tapset0; r[6] = (float)tapset1; r[7] = (float)sidx;
         g_rec.clen += 8;
     }
 }
 
-static int g_last_pre_skip, g_last_output_gain;
+static int g_last_pre_skip, g_last_output_gain, g_last_streams, g_last_coupled, g_last_channels;
+static unsigned char g_last_mapping[256];
 NQREF_API int nqref_last_pre_skip(void) { return g_last_pre_skip; }
 NQREF_API int nqref_last_output_gain(void) { return g_last_output_gain; }
+/* OpusHead layout of the file decoded last: returns channels, fills streams / coupled / mapping[channels] */
+NQREF_API int nqref_last_layout(int *streams, int *coupled, unsigned char *mapping)
+{
+    *streams = g_last_streams; *coupled = g_last_coupled;
+    memcpy(mapping, g_last_mapping, (size_t)g_last_channels);
+    return g_last_channels;
+}
 NQREF_API size_t nqref_comb_floats(void) { return g_rec.clen; }
 NQREF_API void nqref_comb_copy(float *dst) { memcpy(dst, g_rec.cbuf, g_rec.clen * sizeof(float)); }
 
@@ -289,6 +305,11 @@ NQREF_API long nqref_decode_memory(const unsigned char *data, size_t nbytes,
     ch = op_head(of, 0)->channel_count;
     g_last_pre_skip = (int)op_head(of, 0)->pre_skip;
     g_last_output_gain = op_head(of, 0)->output_gain;
+    g_last_streams = op_head(of, 0)->stream_count;
+    g_last_coupled = op_head(of, 0)->coupled_count;
+    g_last_channels = ch;
+    memcpy(g_last_mapping, op_head(of, 0)->mapping, (size_t)(ch < 8 ? ch : 8));
+    g_ndecoders = 0;
     if (channels_out) *channels_out = ch;
     g_rec.active = record; g_rec.len = 0; g_rec.clen = 0; g_rec.nrecords = 0; g_rec.b = 0;
     for (;;) {
@@ -309,6 +330,85 @@ NQREF_API long nqref_decode_memory(const unsigned char *data, size_t nbytes,
     g_rec.active = 0;
     op_free(of);
     return total;
+}
+
+/* ---- an Ogg Opus multistream file made with the reference's own ENCODER --------------------
+ * The reference mount lacks its 8-channel test file (test_data/Rachel8ch.opus is listed in
+ * .MISSING_LARGE_BLOBS), so BASELINE config 4 is exercised on a file produced here: the bundled
+ * libopus surround encoder (opus_multistream_encoder.c:557, mapping family 1, CELT-only through
+ * OPUS_APPLICATION_RESTRICTED_LOWDELAY) + the bundled libogg for the container (RFC 7845:
+ * OpusHead, OpusTags, audio pages with 48 kHz granule positions).
+ * pcm [nsamples][channels] float, 20 ms frames.  Returns the number of bytes written to out
+ * (<0 on error). */
+static int put_page(ogg_stream_state *os, int flush, unsigned char *out, long cap, long *pos)
+{
+    ogg_page og;
+    while (flush ? ogg_stream_flush(os, &og) : ogg_stream_pageout(os, &og)) {
+        if (*pos + og.header_len + og.body_len > cap) return -1;
+        memcpy(out + *pos, og.header, (size_t)og.header_len); *pos += og.header_len;
+        memcpy(out + *pos, og.body, (size_t)og.body_len); *pos += og.body_len;
+    }
+    return 0;
+}
+
+NQREF_API long nqref_encode_surround(const float *pcm, long nsamples, int channels, int bitrate,
+                                     unsigned char *out, long cap)
+{
+    int err = 0, streams = 0, coupled = 0, lookahead = 0, i;
+    unsigned char mapping[255], head[32 + 255], pkt[8 * 1500];
+    const char *vendor = "nq-oracle";
+    unsigned char tags[64];
+    long pos = 0, f, nframes = nsamples / FRAME;
+    ogg_stream_state os;
+    ogg_packet op;
+    OpusMSEncoder *enc = opus_multistream_surround_encoder_create(48000, channels, channels > 2 ? 1 : 0, &streams, &coupled,
+                                                                  mapping, OPUS_APPLICATION_RESTRICTED_LOWDELAY, &err);
+    if (!enc || err != OPUS_OK) return -1;
+    opus_multistream_encoder_ctl(enc, OPUS_SET_BITRATE(bitrate));
+    opus_multistream_encoder_ctl(enc, OPUS_GET_LOOKAHEAD(&lookahead));
+    if (ogg_stream_init(&os, 0x0B200) != 0) return -2;
+    /* OpusHead, RFC 7845 section 5.1 */
+    memcpy(head, "OpusHead", 8);
+    head[8] = 1; head[9] = (unsigned char)channels;
+    head[10] = (unsigned char)(lookahead & 255); head[11] = (unsigned char)(lookahead >> 8);
+    head[12] = 0x80; head[13] = 0xBB; head[14] = 0; head[15] = 0;   /* 48000 */
+    head[16] = 0; head[17] = 0;                                     /* output gain 0 */
+    head[18] = (unsigned char)(channels > 2 ? 1 : 0);
+    i = 19;
+    if (channels > 2) {
+        head[i++] = (unsigned char)streams; head[i++] = (unsigned char)coupled;
+        memcpy(head + i, mapping, (size_t)channels); i += channels;
+    }
+    memset(&op, 0, sizeof op);
+    op.packet = head; op.bytes = i; op.b_o_s = 1; op.packetno = 0;
+    ogg_stream_packetin(&os, &op);
+    if (put_page(&os, 1, out, cap, &pos)) return -3;
+    /* OpusTags, section 5.2 */
+    memcpy(tags, "OpusTags", 8);
+    i = (int)strlen(vendor);
+    tags[8] = (unsigned char)i; tags[9] = tags[10] = tags[11] = 0;
+    memcpy(tags + 12, vendor, (size_t)i);
+    memset(tags + 12 + i, 0, 4);
+    memset(&op, 0, sizeof op);
+    op.packet = tags; op.bytes = 16 + i; op.packetno = 1;
+    ogg_stream_packetin(&os, &op);
+    if (put_page(&os, 1, out, cap, &pos)) return -3;
+    for (f = 0; f < nframes; f++) {
+        int n = opus_multistream_encode_float(enc, pcm + f * FRAME * channels, FRAME, pkt, (opus_int32)sizeof pkt);
+        if (n < 0) return -4;
+        memset(&op, 0, sizeof op);
+        op.packet = pkt; op.bytes = n; op.packetno = 2 + f;
+        op.e_o_s = f == nframes - 1;
+        /* granule position = samples up to and including this packet; the last one is trimmed so the
+         * file plays nsamples - lookahead... keep every decoded sample: total = all frames - pre-skip */
+        op.granulepos = (f + 1) * FRAME;
+        ogg_stream_packetin(&os, &op);
+        if (put_page(&os, 0, out, cap, &pos)) return -3;
+    }
+    if (put_page(&os, 1, out, cap, &pos)) return -3;
+    ogg_stream_clear(&os);
+    opus_multistream_encoder_destroy(enc);
+    return pos;
 }
 
 NQREF_API long nqref_record_count(void) { return g_rec.nrecords; }

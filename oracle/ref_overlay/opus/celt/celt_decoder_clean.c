@@ -19,12 +19,12 @@ void nqref_tap_mdct(const mdct_lookup *l, float *in, float *out,
 
 /* comb_filter (celt.c:114) is called twice per channel per frame at
  * celt_decoder_clean.c:663-669; the tap logs the arguments and calls through. */
-void nqref_tap_comb_filter(float *y, float *x, int T0, int T1, int N, float g0, float g1,
+void nqref_tap_comb_filter(const void *decoder, float *y, float *x, int T0, int T1, int N, float g0, float g1,
                            int tapset0, int tapset1, const float *window, int overlap);
 
 #define clt_mdct_backward_B1_C2 nqref_tap_mdct_b1c2
 #define clt_mdct_backward nqref_tap_mdct
-#define comb_filter nqref_tap_comb_filter
+#define comb_filter(...) nqref_tap_comb_filter((const void *)st, __VA_ARGS__)   /* st: the CELTDecoder in scope at :663-669 */
 #include_next "opus/celt/celt_decoder_clean.c"
 #undef clt_mdct_backward_B1_C2
 #undef clt_mdct_backward

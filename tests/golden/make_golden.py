@@ -16,6 +16,9 @@ Outputs (all small):
                      call sites while the reference decodes the bundled
                      sb-reverie.opus / sb-reverie-60ms-frames.opus / short.opus
                      (coefficients in, out_syn out), incl. transient frames
+  surround8.opus     BASELINE config 4 stand-in for the missing Rachel8ch.opus: a 7.1 Ogg Opus file made
+                     with the reference's own surround encoder from seeded synthetic audio
+                     (+ surround8.json: what the reference decoder makes of it)
   post_cases.npz     SURVEY.md 8(f) row 1: single comb_filter / deemphasis calls of
                      the compiled reference on seeded inputs, and the LAST 26 frames
                      of short.opus (active post-filter, tapset changes, a transient
@@ -146,6 +149,34 @@ def main():
             post["short_tail.transient"] = np.array([r["B"] == 8 for r in recs[k:]], np.uint8)
             post["short_tail.coef_first"] = recs[k]["coef"]
     np.savez_compressed(f"{HERE}/post_cases.npz", **post)
+
+    # BASELINE config 4: the reference mount lacks test_data/Rachel8ch.opus (.MISSING_LARGE_BLOBS), so an
+    # 8-channel (7.1: 3 coupled + 2 mono streams) Ogg Opus file is made with the reference's own surround
+    # ENCODER + libogg (oracle/ref_harness.c nqref_encode_surround) from seeded synthetic audio: tones,
+    # noise and percussive bursts at channel-dependent times, so every stream switches blocks on its own.
+    fs, secs, ch = 48000, 6, 8
+    n = (fs * secs // 960) * 960
+    t = np.arange(n) / fs
+    r8 = np.random.default_rng(8)
+    pcm8 = np.zeros((n, ch), np.float32)
+    for c in range(ch):
+        f0 = 110.0 * (c + 2)
+        x = 0.25 * np.sin(2 * np.pi * f0 * t) + 0.1 * np.sin(2 * np.pi * f0 * 2.01 * t) + 0.02 * r8.standard_normal(n)
+        for k in range(12):
+            p0 = int((0.3 + 0.45 * k + 0.037 * c) * fs)
+            if p0 + 2000 < n:
+                x[p0:p0 + 2000] += 0.6 * r8.standard_normal(2000) * np.exp(-np.arange(2000) / 300.0)
+        pcm8[:, c] = x
+    data = ref.encode_surround(np.clip(pcm8, -0.95, 0.95).astype(np.float32), 512000)
+    open(f"{HERE}/surround8.opus", "wb").write(data)
+    out8, recs8 = ref.decode_bytes(data, record=True)
+    assert ref.layout_info() == (8, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7]) and out8.shape == (n - 120, 8)
+    import hashlib
+    import json
+    json.dump({"samples_per_channel": int(out8.shape[0]), "channels": 8, "records": len(recs8),
+               "transient_records": int(sum(r["B"] == 8 for r in recs8)),
+               "reference_pcm_sha256": hashlib.sha256(out8.tobytes()).hexdigest()},
+              open(f"{HERE}/surround8.json", "w"), indent=1)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -227,3 +227,23 @@ def test_whole_file_pcm_vs_reference_decoder(synth, fname):
     s = float(np.cumsum(flat, dtype=np.float32)[-1])
     print(f"{fname}: max |err| {err:.2e}, sum {s:.4f}, len {flat.size}")
     assert (int(s), flat.size) == CHECKSUMS[fname]
+
+
+def test_surround8_whole_file_multistream_decode(synth):
+    """BASELINE config 4 (stand-in for the missing Rachel8ch.opus, made with the reference's own
+    surround encoder): phase 1 = the reference decoder recording all 5 streams, phase 2 = ONE GPU
+    call -- 5 streams in 4 warps, the 7.1 channel mapping fused into the synthesis store pass, post
+    stage per output channel -- against the reference decoder's own 8-channel PCM."""
+    from conftest import GOLDEN
+    from ms_helpers import multistream_batch
+    path = os.path.join(GOLDEN, "surround8.opus")
+    if not ref.available():
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    pcm_ref, recs = ref.decode_file(path, record=True)
+    ch, streams, coupled, mapping = ref.layout_info()
+    pre_skip, gain = ref.header_info()
+    assert (ch, streams, coupled, gain) == (8, 5, 3, 0)
+    coef, flags, frames = multistream_batch(recs, streams, coupled)
+    got, _ = synth.decode_batch(coef, flags, frames, streams=streams, coupled_streams=coupled, mapping=mapping)
+    err = assert_pcm(pcm_ref, got[pre_skip:pre_skip + len(pcm_ref)], "surround8.opus")
+    print(f"surround8.opus: {coef.shape[0]} frames x 5 streams, max |err| {err:.2e}")

@@ -74,6 +74,28 @@ def test_nyquistio_load_two_phase_matches_reference(twophase, fname):
           f"max |err| {err:.2e}, sum {s:.4f}")
 
 
+def test_nyquistio_load_two_phase_8_channel_multistream(twophase):
+    """BASELINE config 4 through nqr::NyquistIO::Load: 7.1 file (3 coupled + 2 mono streams, made
+    with the reference's own encoder; the reference mount lacks Rachel8ch.opus)."""
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "surround8.opus")
+    load(twophase, path)
+    got, ch, sr, tm, wall = load(twophase, path)
+    assert got is not None and (ch, sr) == (8, 48000)
+    if ref.load_available():
+        want, _, t_ref = ref.nyquist_load(path)
+    elif ref.available():
+        want, _ = ref.decode_file(path)
+        t_ref = float("nan")
+    else:
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    assert got.shape == want.shape
+    err = float(np.abs(got.astype(np.float64) - want).max())
+    assert err <= 1e-5 and snr_db(want, got) >= 100.0, err
+    print(f"\nsurround8.opus: Load {wall * 1e3:.0f} ms (phase 1 {tm[0] * 1e3:.0f} ms, phase 2 tail {tm[1] * 1e3:.0f} ms) "
+          f"vs reference Load {t_ref * 1e3:.0f} ms; max |err| {err:.2e}")
+
+
 def test_two_phase_load_errors_like_the_reference(twophase, tmp_path):
     bad = tmp_path / "noise.opus"
     bad.write_bytes(np.random.default_rng(0).integers(0, 256, 5000, dtype=np.uint8).tobytes())

@@ -86,3 +86,27 @@ def test_live_whole_file_pcm_bit_exact_short_opus():
     sig = np.concatenate([r["out"].T for r in recs], axis=0)
     full, _, _ = port.post_batch(sig, port.post_frames_from_records(recs))
     assert np.array_equal(full[pre_skip:pre_skip + len(pcm)].view(np.uint32), pcm.view(np.uint32))
+
+
+# ---- BASELINE config 4: 8-channel multistream file (stand-in for the missing Rachel8ch.opus) ----
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnq_ref.so not built (needs /root/reference)")
+def test_surround8_reference_decode_is_pinned_and_oracle_reproduces_it_bit_exactly():
+    """tests/golden/surround8.opus was made with the reference's own surround encoder.  The
+    reference decoder's PCM for it is pinned by hash; the oracle (per-stream synthesis + post stage
+    + opus_multistream channel routing) reproduces that PCM bit for bit, mono streams included."""
+    import hashlib
+    import json
+    from conftest import GOLDEN
+    from ms_helpers import multistream_batch, oracle_decode_multistream
+    meta = json.load(open(os.path.join(GOLDEN, "surround8.json")))
+    pcm, recs = ref.decode_file(os.path.join(GOLDEN, "surround8.opus"), record=True)
+    assert pcm.shape == (meta["samples_per_channel"], meta["channels"]) and len(recs) == meta["records"]
+    assert hashlib.sha256(pcm.tobytes()).hexdigest() == meta["reference_pcm_sha256"]
+    ch, streams, coupled, mapping = ref.layout_info()
+    assert (ch, streams, coupled, mapping) == (8, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7])
+    pre_skip, gain = ref.header_info()
+    coef, flags, frames = multistream_batch(recs, streams, coupled)
+    assert (flags >> 1 == 0).all() and (flags & 1).sum() == meta["transient_records"]
+    assert len({tuple(flags[f]) for f in range(len(flags))}) > 4, "streams should switch blocks independently"
+    full = oracle_decode_multistream(coef, flags, frames, streams, coupled, mapping)
+    assert np.array_equal(full[pre_skip:pre_skip + len(pcm)].view(np.uint32), pcm.view(np.uint32))
