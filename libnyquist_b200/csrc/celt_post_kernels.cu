@@ -121,7 +121,7 @@ __device__ __forceinline__ int stage_at(int n) { return (n >> 3) * (8 * NCH + kS
 // t < 120 owns samples [t*seg, (t+1)*seg), seg = N/120; the segment carries (affine maps
 // m -> m_seg + a^seg m) are combined by a warp scan plus a 4-entry hand-over between the warps.
 template <int NCH>
-__device__ __forceinline__ void deemphasis_frame(PostSmem &sm, int N, int tid)
+__device__ __forceinline__ void deemphasis_frame(PostSmem &sm, int N, int tid, float Al8)
 {
     constexpr float a = 0.85000610f;   // mode->preemph[0], static_modes_float.h:583
     const int seg = N / kPostSegs;     // 8, 4, 2, 1
@@ -172,8 +172,11 @@ __device__ __forceinline__ void deemphasis_frame(PostSmem &sm, int N, int tid)
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++) sm.wtot[ch][warp] = m[ch];
     __syncthreads();
-    float Al = 1.f;         // A^lane
-    for (int k = 0; k < lane; k++) Al *= A;
+    float Al = Al8;         // A^lane; precomputed by the caller for 20 ms frames
+    if (!fast) {
+        Al = 1.f;
+        for (int k = 0; k < lane; k++) Al *= A;
+    }
 #pragma unroll
     for (int ch = 0; ch < NCH; ch++) {
         float cw = 0.f;     // state entering this warp's first segment
@@ -226,6 +229,14 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
     __syncthreads();
     long long s0 = job.sample0;
     const PostFrame *fr = p.frames + (size_t)job.frame0 * p.frame_stride + job.stream_col;
+    // (0.85000610^8)^lane: how far the de-emphasis state entering this thread's warp decays before its
+    // segment of a 20 ms frame (deemphasis_frame); a chain of up to 31 dependent multiplies, done once
+    float Al8 = 1.f;
+    {
+        float A8 = 0.85000610f;
+        A8 *= A8; A8 *= A8; A8 *= A8;
+        for (int k = 0; k < (tid & 31); k++) Al8 *= A8;
+    }
     // Plain stereo, 20 ms frames (the common case): the NEXT frame's 7680 bytes are fetched into
     // registers before the current frame is filtered, so the HBM latency hides behind the
     // recurrences instead of adding to every frame.  480 float4 = 120 threads x 4.
@@ -300,7 +311,7 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
                 if (N > mid) comb_region<NCH>(sm, mid, N, tcur, tnew, false, tid);
             }
         }
-        deemphasis_frame<NCH>(sm, N, tid);
+        deemphasis_frame<NCH>(sm, N, tid, Al8);
         // staging -> HBM, scaled to [-1, 1] (SCALEOUT, arch.h:202)
         constexpr float kScale = 1.f / 32768.f;
         if (NCH == 2 && C == 2) {

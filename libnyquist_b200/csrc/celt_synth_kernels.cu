@@ -90,7 +90,6 @@ struct __align__(16) WarpSmem {
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp smem slice must keep 16-byte alignment");
 static_assert((kInRowFloats * 4) % 16 == 0, "TMA destination rows must be 16-byte aligned");
 
-constexpr int kWarpSmemFloats = int(sizeof(WarpSmem) / 4);
 constexpr int kPlaneOffFloats = 2 * kInRowFloats;   // offsetof(WarpSmem, x) / 4
 
 // This file is compiled four times (-DNQ_PART=0..3, libnyquist_b200/build.py) so the kernel
