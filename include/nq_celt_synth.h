@@ -76,7 +76,10 @@ NQ_API void nq_celt_host_free(void *p);
  *              denormalise_bands leaves them in freq[] (channel-major; a
  *              transient frame keeps its 8 sub-blocks interleaved,
  *              freq[c*960 + j*8 + b], celt_decoder_clean.c:296)
- *   transient  [nframes]          non-zero => shortBlocks = 8 for that frame
+ *   transient  [nframes]          flag byte per frame: 0 = long block, 1 = isTransient
+ *              (shortBlocks = 8; celt_decoder_clean.c:586, :656).  Other bits are
+ *              optional extensions, see nq_celt_synth_batch_device_ms: bits 1-2 =
+ *              3 - LM (with frame_offset), bit 3 = decoder reset before the frame
  *   tail_in    [C][60] or NULL    raw tail left by the frame before the batch
  *              (= out_syn[c][960..1020) after that frame); NULL => zeros,
  *              i.e. a freshly reset decoder (celt_decoder_clean.c:846-859)
