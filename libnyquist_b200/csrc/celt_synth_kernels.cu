@@ -178,66 +178,76 @@ __device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *fram
     }
 }
 
-// ------------------------------------------------------------ long frame ---
-// One stereo (or mono: nch == 1) long block per call.  See file header.
-template <int kModeT>
-__device__ __forceinline__ void long_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off,
-                                           int cb, int nch, bool store, bool more, long long fnext,
-                                           const float (&w4)[4], GroupCtx &grp, int vmask, int next_nch)
+// ------------------------------------------------- prefetch of the next item ---
+// TMA bulk copies of the next item's coefficient rows into ws.in (lane 0 issues, completion on
+// the warp's mbarrier).  Only once every lane is done with ws.in.
+__device__ __forceinline__ void prefetch_rows(const SynthParams &p, WarpSmem &ws, int lane, long long fnext, int cb, int rows)
 {
-    // kModeMono: the two "channels" are two CONSECUTIVE FRAMES of one mono stream (rows f and f+1
-    // of the coefficient array), so a mono stream fills the warp like a stereo one; channel 1 then
-    // overlap-adds against channel 0's fresh tail instead of a stored one.  next_nch = rows to
-    // prefetch for the next item (1 or 2 frames there; == nch in every other mode).
-    // vmask (group mode): bit ch set = channel ch of this warp is a long block in this frame.  Two
-    // mono streams that share a warp switch blocks independently; when they disagree the frame is
-    // run through long_frame and short_frame once each and each keeps only its own channel.
-    constexpr bool kPaired = kModeT == kModeGroupPaired;
-    constexpr int kMode = kPaired ? kModeGroup : kModeT;
-    constexpr bool kStereo = kMode == kModeStereo;
-    if (!kPaired) vmask = 3;
+    if (lane == 0) {
+        mbar_expect_tx(&ws.bar, rows * kFrame * 4);
+        for (int ch = 0; ch < rows; ch++) {
+            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + (cb + ch) * kFrame;
+            tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- stage 1 ---
+// Common to long and transient frames -- ONE copy of the 30-point transform in the instruction
+// cache, which the two paths do not fit together otherwise (20 % transient frames: 37 % i-cache
+// misses with separate copies).  Lane = (channel c, r):
+//   long block : r = residue n2, bins i = 16 n1 + n2;  x[2i] = X[32 n1 + 2 n2], x[959-2i] = X[959 - 2 n2 - 32 n1]
+//   short block: r = 2b + h (sub-block b, half h), bins i = 2 n1 + h of the 60-point transform of sub-block b;
+//                x[2i] = X[b + 8 (4 n1 + 2h)], x[119-2i] = X[b + 8 (119 - 4 n1 - 2h)]   (celt_decoder_clean.c:296)
+// i.e. both read xa = row[oa + 32 n1], xb = row[ob - 32 n1] with lane-dependent (oa, ob), rotate by the
+// literal exp(j 2pi n1/120) [mdct.c:303-312 without the lane-constant part], run the 30-point DFT and
+// multiply by a lane-dependent row of a twiddle table (rotations + inter-stage twiddle folded, DESIGN.md
+// section 3); the products go to the transpose buffer ws.x[c][r][k1].
+template <int kModeT>
+__device__ __forceinline__ void stage1_common(const FastTables &tb, WarpSmem &ws, int lane, bool is_short, GroupCtx &grp)
+{
+    constexpr int kMode = kModeT == kModeGroupPaired ? kModeGroup : kModeT;
     constexpr float pre_re[30] = {NQ_PRE30_RE};
     constexpr float pre_im[30] = {NQ_PRE30_IM};
-    constexpr float post_re[16] = {NQ_POST16_RE};
-    constexpr float post_im[16] = {NQ_POST16_IM};
-
-    // ---- stage 1: lane = (channel c1, residue n2); bins i = 16*n1 + n2 ----
-    const int c1 = lane >> 4, n2 = lane & 15;
+    const int c = lane >> 4, r = lane & 15, b = r >> 1, h = r & 1;
+    const int oa = is_short ? 16 * h + b : 2 * r;
+    const int ob = is_short ? 952 + b - 16 * h : 959 - 2 * r;
+    const float *row = ws.in + c * kInRowFloats;
     float2 g[30];
-    {
-        const float2 *row = reinterpret_cast<const float2 *>(ws.in + c1 * kInRowFloats) + n2;
-        float2 v[30];
 #pragma unroll
-        for (int n1 = 0; n1 < 30; n1++) v[n1] = row[16 * n1];   // (X[2i], X[2i+1])
-        // X[N2-1-2i] is the odd element of bin 479-i = 16*(29-n1) + (15-n2): mirrored lane, mirrored slot
-#pragma unroll
-        for (int n1 = 0; n1 < 30; n1++) {
-            const float xb = __shfl_xor_sync(kFull, v[29 - n1].y, 15);
-            const float xa = v[n1].x;
-            // (xb + j xa) * exp(j 2pi n1 / 120)   [mdct.c:303-312 without the lane-constant part]
-            g[n1] = make_float2(fmaf(xb, pre_re[n1], -(xa * pre_im[n1])), fmaf(xb, pre_im[n1], xa * pre_re[n1]));
-        }
+    for (int n1 = 0; n1 < 30; n1++) {
+        const float xa = row[oa + 32 * n1], xb = row[ob - 32 * n1];
+        g[n1] = make_float2(fmaf(xb, pre_re[n1], -(xa * pre_im[n1])), fmaf(xb, pre_im[n1], xa * pre_re[n1]));
     }
     idft30(g);
     if (kMode == kModeGroup && grp.pending) {   // the group's previous store pass reads ws.x of every warp
         group_sync(grp);
         grp.pending = false;
     }
-    {
-        const float2 *tw = tb.t_long + n2 * kXRowF2;
-        float2 *dst = ws.x + c1 * kXChanF2 + n2 * kXRowF2;
+    const float2 *tw = is_short ? tb.t_short + h * 30 : tb.t_long + r * kXRowF2;
+    float2 *dst = ws.x + c * kXChanF2 + r * kXRowF2;
 #pragma unroll
-        for (int k1 = 0; k1 < 30; k1++) dst[k1] = cmul(g[k1], tw[k1]);
-    }
-    __syncwarp();
-    // every lane has consumed its part of ws.in: prefetch the next frame
-    if (more && lane == 0) {
-        mbar_expect_tx(&ws.bar, next_nch * kFrame * 4);
-        for (int ch = 0; ch < next_nch; ch++) {
-            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + (cb + ch) * kFrame;
-            tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
-        }
-    }
+    for (int k1 = 0; k1 < 30; k1++) dst[k1] = cmul(g[k1], tw[k1]);
+    __syncwarp();   // ws.in is consumed, ws.x is complete
+}
+
+// ------------------------------------------------------ long block, stage 2 ---
+// kModeMono: the two "channels" are two CONSECUTIVE FRAMES of one mono stream (rows f and f+1 of
+// the coefficient array), so a mono stream fills the warp like a stereo one; channel 1 then
+// overlap-adds against channel 0's fresh tail instead of a stored one.
+// vmask (paired group mode): bit ch set = channel ch of this warp is a long block in this frame.
+// Two mono streams that share a warp switch blocks independently; when they disagree the frame
+// goes through both paths and each keeps only its own channel.
+template <int kModeT>
+__device__ __forceinline__ void long_stage2(const SynthParams &p, WarpSmem &ws, int lane, long long off, int cb, int nch,
+                                            bool store, const float (&w4)[4], int vmask)
+{
+    constexpr bool kPaired = kModeT == kModeGroupPaired;
+    constexpr int kMode = kPaired ? kModeGroup : kModeT;
+    constexpr bool kStereo = kMode == kModeStereo;
+    if (!kPaired) vmask = 3;
+    constexpr float post_re[16] = {NQ_POST16_RE};
+    constexpr float post_im[16] = {NQ_POST16_IM};
 
     // ---- stage 2: lane = k1 (30 active); bins k = k1 + 30*k2, both channels ----
     const bool active = lane < 30;
@@ -367,115 +377,87 @@ __device__ __forceinline__ void long_frame(const SynthParams &p, const FastTable
     }
 }
 
-// ------------------------------------------------------ transient frame ----
-// 8 short blocks per channel (N = 240, N2 = 120, N4 = 60), sub-block b uses
-// coefficients X[b + 8j] (celt_decoder_clean.c:292-300).
+// ---------------------------------------------------- short blocks, stage 2 ---
+// 8 short blocks per channel (N = 240, N2 = 120, N4 = 60).  The radix-2 step that completes the
+// 60-point transform pairs the rows r and r^1 of the transpose buffer; window + overlap-add against
+// the previous sub-block's raw tail (lane - 2, a shuffle) follow.  A ROLLED loop over k1 (the inputs
+// sit in shared memory, not in registers): a few hundred bytes of code instead of 12 KB.  The
+// finished samples wait in the channel's own -- consumed -- coefficient row, ws.in[c][0..960).
 template <int kModeT>
-__device__ __forceinline__ void short_frame(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off,
-                                            int cb, int nch, bool store, bool more, long long fnext, GroupCtx &grp, int vmask,
-                                            int next_nch)
+__device__ __forceinline__ void short_stage2(const FastTables &tb, WarpSmem &ws, int lane, int nch, int vmask)
 {
     constexpr bool kPaired = kModeT == kModeGroupPaired;
     constexpr int kMode = kPaired ? kModeGroup : kModeT;
-    constexpr bool kStereo = kMode == kModeStereo;
-    constexpr float pre_re[30] = {NQ_PRE30_RE};
-    constexpr float pre_im[30] = {NQ_PRE30_IM};
-
-    // lane = (channel c, sub-block b, half h); bins i = 2*n1 + h
-    const int c = lane >> 4, b = (lane >> 1) & 7, h = lane & 1;
-    const bool mine = !kPaired || ((vmask >> c) & 1);   // see long_frame: bit c = this channel is transient here
-    float2 g[30];
-    {
-        const float *row = ws.in + c * kInRowFloats + b;
-#pragma unroll
-        for (int n1 = 0; n1 < 30; n1++) {
-            const float xa = row[32 * n1 + 16 * h];              // x[2i]     = X[b + 8*2i]
-            const float xb = row[952 - 32 * n1 - 16 * h];        // x[119-2i] = X[b + 8*(119-2i)]
-            g[n1] = make_float2(fmaf(xb, pre_re[n1], -(xa * pre_im[n1])), fmaf(xb, pre_im[n1], xa * pre_re[n1]));
+    const int c = lane >> 4, r = lane & 15, b = r >> 1, h = r & 1;
+    const bool mine = !kPaired || ((vmask >> c) & 1);   // bit c = this channel is transient in this frame
+    const float2 *a_own = ws.x + c * kXChanF2 + r * kXRowF2;
+    const float2 *a_oth = ws.x + c * kXChanF2 + (r ^ 1) * kXRowF2;
+    float *stage = ws.in + c * kInRowFloats + 120 * b;
+    // kModeMono: c = 1 is the NEXT frame of the same stream; its block 0 follows block 7 of c = 0 (lane - 2)
+    float *tail = ws.tail + (kMode == kModeMono ? 0 : c * kHalfOvl);
+    const bool tail_from_smem = b == 0 && (kMode != kModeMono || c == 0);
+    const bool tail_writer = b == 7 && (kMode == kModeMono ? c == nch - 1 : mine);
+    // Y = Z * exp(j 2pi 30 h / 240); y[2k] = -Re Y, y[119-2k] = Im Y with bins k = k1 + 30 h
+    //   h = 0: head = y[2k1],    tl = y[119-2k1]
+    //   h = 1: head = y[59-2k1], tl = y[60+2k1]
+    const float dr = h ? NQ_SQRT1_2 : 1.0f, di = h ? NQ_SQRT1_2 : 0.0f;
+#pragma unroll 5
+    for (int k1 = 0; k1 < 30; k1++) {
+        const float2 a = a_own[k1], pa = a_oth[k1];
+        const float2 z = h ? csub(pa, a) : cadd(a, pa);
+        const float yr = fmaf(z.x, dr, -(z.y * di)), yi = fmaf(z.x, di, z.y * dr);
+        const float head = h ? yi : -yr, tl = h ? -yr : yi;
+        const int m = h ? 59 - 2 * k1 : 2 * k1;      // head = y[m]
+        float tp = __shfl_up_sync(kFull, tl, 2);     // same (c, h), sub-block b-1
+        if (tail_from_smem) tp = tail[59 - m];
+        const float wlo = tb.window[59 - m], whi = tb.window[60 + m];
+        if (mine) {
+            stage[59 - m] = fmaf(whi, tp, -(wlo * head));   // out[59-m]
+            stage[60 + m] = fmaf(wlo, tp, whi * head);      // out[60+m]
         }
-    }
-    idft30(g);
-    // radix-2 step across the lane pair (h = 0, 1); bins k = k1 + 30*h
-    // Y = Z * exp(j 2pi 30 h / 240); y[2k] = -Re Y, y[119-2k] = Im Y
-    // h = 0: head[k1] = y[2k1],      tl[k1] = y[119-2k1]
-    // h = 1: head[k1] = y[59-2k1],   tl[k1] = y[60+2k1]
-    float head[30], tl[30];
-    {
-        const float2 *tw = tb.t_short + h * 30;
-        const float dr = h ? NQ_SQRT1_2 : 1.0f, di = h ? NQ_SQRT1_2 : 0.0f;
-#pragma unroll
-        for (int k1 = 0; k1 < 30; k1++) {
-            const float2 a = cmul(g[k1], tw[k1]);
-            const float2 pa = make_float2(__shfl_xor_sync(kFull, a.x, 1), __shfl_xor_sync(kFull, a.y, 1));
-            const float2 z = h ? csub(pa, a) : cadd(a, pa);
-            const float yr = fmaf(z.x, dr, -(z.y * di)), yi = fmaf(z.x, di, z.y * dr);
-            head[k1] = h ? yi : -yr;
-            tl[k1] = h ? -yr : yi;
-        }
+        __syncwarp();                                // the old tail entry is consumed ...
+        if (tail_writer) tail[59 - m] = tl;          // ... before block 7 replaces it: y_7[60 + (59-m)]
     }
     __syncwarp();
-    if (more && lane == 0) {
-        mbar_expect_tx(&ws.bar, next_nch * kFrame * 4);
-        for (int ch = 0; ch < next_nch; ch++) {
-            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + (cb + ch) * kFrame;
-            tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
+}
+
+// Finished short-block frame: planar ws.in[c][0..960) -> where the mode wants it.
+template <int kModeT>
+__device__ __forceinline__ void short_output(const SynthParams &p, WarpSmem &ws, int lane, long long off, int cb, int nch, bool store)
+{
+    constexpr int kMode = kModeT == kModeGroupPaired ? kModeGroup : kModeT;
+    const float *L = ws.in, *R = ws.in + kInRowFloats;
+    if (kMode == kModeGroup) {   // the stream's [960][2] plane for the group's store pass
+        float4 *pl = reinterpret_cast<float4 *>(ws.x);
+#pragma unroll 5
+        for (int j = 0; j < 15; j++) {
+            const int n = 2 * (lane + 32 * j);
+            const float2 l = *reinterpret_cast<const float2 *>(L + n), rr = *reinterpret_cast<const float2 *>(R + n);
+            pl[n >> 1] = make_float4(l.x, rr.x, l.y, rr.y);
+        }
+    } else if (!store) {
+    } else if (kMode == kModeStereo) {
+        float4 *dst = reinterpret_cast<float4 *>(p.pcm + off * 2);
+#pragma unroll 5
+        for (int j = 0; j < 15; j++) {
+            const int n = 2 * (lane + 32 * j);
+            const float2 l = *reinterpret_cast<const float2 *>(L + n), rr = *reinterpret_cast<const float2 *>(R + n);
+            __stcs(dst + (n >> 1), make_float4(l.x, rr.x, l.y, rr.y));
+        }
+    } else if (kMode == kModeMono) {
+        for (int ch = 0; ch < nch; ch++) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(ws.in + ch * kInRowFloats);
+            float4 *dst = reinterpret_cast<float4 *>(p.pcm + off + ch * kFrame);
+            for (int j = lane; j < kFrame / 4; j += 32) __stcs(dst + j, s4[j]);
+        }
+    } else {   // kModeDirect
+        float *dst = p.pcm + off * p.C + cb;
+        for (int idx = lane; idx < 2 * kFrame; idx += 32) {
+            const int n = idx >> 1, ch = idx & 1;
+            if (ch < nch) dst[n * p.C + ch] = ws.in[ch * kInRowFloats + n];
         }
     }
-    if (kMode == kModeGroup && grp.pending) {   // see long_frame
-        group_sync(grp);
-        grp.pending = false;
-    }
-    // window + overlap-add against the previous sub-block's raw tail
-    float *stage = reinterpret_cast<float *>(ws.x);   // [n][2] interleaved
-#pragma unroll
-    for (int k1 = 0; k1 < 30; k1++) {
-        const int m = h ? 59 - 2 * k1 : 2 * k1;      // head[k1] = y[m]
-        float tp = __shfl_up_sync(kFull, tl[k1], 2);  // same (c, h), sub-block b-1
-        // kModeMono: c = 1 is the NEXT frame of the same stream; its block 0 follows block 7 of c = 0 (lane - 2)
-        if (b == 0 && (kMode != kModeMono || c == 0)) tp = ws.tail[(kMode == kModeMono ? 0 : c * kHalfOvl) + 59 - m];
-        const float wlo = tb.window[59 - m], whi = tb.window[60 + m];
-        const float olo = fmaf(whi, tp, -(wlo * head[k1]));   // out[59-m]
-        const float ohi = fmaf(wlo, tp, whi * head[k1]);      // out[60+m]
-        if (kMode == kModeMono) {   // planar: frame c at stage[960 c ..]
-            stage[kFrame * c + 120 * b + 59 - m] = olo;
-            stage[kFrame * c + 120 * b + 60 + m] = ohi;
-        } else if (mine) {
-            stage[(120 * b + 59 - m) * 2 + c] = olo;
-            stage[(120 * b + 60 + m) * 2 + c] = ohi;
-        }
-    }
-    __syncwarp();   // old frame tail fully consumed, staging complete
-    if (b == 7 && (kMode == kModeMono ? c == nch - 1 : mine)) {
-#pragma unroll
-        for (int k1 = 0; k1 < 30; k1++) {
-            const int m = h ? 59 - 2 * k1 : 2 * k1;
-            ws.tail[(kMode == kModeMono ? 0 : c * kHalfOvl) + 59 - m] = tl[k1];          // y_7[60 + (59-m)]
-        }
-    }
-    if (store && kMode == kModeMono) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(stage);
-        float4 *dst = reinterpret_cast<float4 *>(p.pcm + off);
-        for (int j = lane; j < nch * (kFrame / 4); j += 32) __stcs(dst + j, s4[j]);
-    } else if (store && kMode != kModeGroup) {   // group mode: `stage` IS the stream's plane, stored by the group
-        if (kStereo) {
-            const float4 *s4 = reinterpret_cast<const float4 *>(stage);
-            float4 *dst = reinterpret_cast<float4 *>(p.pcm + off * 2);
-#pragma unroll
-            for (int j = 0; j < 15; j++) __stcs(dst + lane + 32 * j, s4[lane + 32 * j]);
-        } else {
-            float *dst = p.pcm + off * p.C + cb;
-            if (nch == 2 && (p.C & 1) == 0) {
-                const float2 *s2 = reinterpret_cast<const float2 *>(stage);
-                for (int n = lane; n < kFrame; n += 32) __stcs(reinterpret_cast<float2 *>(dst + n * p.C), s2[n]);
-            } else {
-                for (int idx = lane; idx < 2 * kFrame; idx += 32) {
-                    const int n = idx >> 1, ch = idx & 1;
-                    if (ch < nch) dst[n * p.C + ch] = stage[idx];
-                }
-            }
-        }
-    }
-    __syncwarp();   // staging buffer is reused by the next frame's stage 1
+    __syncwarp();   // ws.in may be refilled
 }
 
 // ------------------------------------------- frames shorter than 20 ms ----
@@ -686,14 +668,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         };
         int nfr = (kMode == kModeMono && mono_pair(f, flag)) ? 2 : 1;
         const int state_nch = nch;   // channels with a tail of their own (kModeMono: nch is reused as frames per item)
-        if (lane == 0) {
-            const int rows = kMode == kModeMono ? nfr : nch;
-            mbar_expect_tx(&ws.bar, rows * kFrame * 4);
-            for (int ch = 0; ch < rows; ch++) {
-                const float *src = (f < 0 ? p.halo_coef : p.coef + f * p.D * kFrame) + (cb + ch) * kFrame;
-                tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
-            }
-        }
+        prefetch_rows(p, ws, lane, f, cb, kMode == kModeMono ? nfr : nch);
         while (f < f1) {
             if (kMode == kModeMono) nch = nfr;
             const bool more = f + nfr < f1;
@@ -714,16 +689,36 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             const int tr0 = flag & 1;
             const bool split = kPaired && tr1 >= 0 && tr1 != tr0;
             if (sh == 0) {
-                // one pass, or (two mono streams that disagree) a long pass for the one and a short
-                // pass for the other; the long pass goes first because it needs ws.x as its transpose
-                // buffer, and only the last pass may release ws.in to the prefetch
+                const int next_nch = kMode == kModeMono ? next_nfr : nch;
+                // One pass -- or, for two mono streams in one warp that disagree about block switching,
+                // two: the short pass goes first and parks its channel's samples in that channel's own
+                // coefficient row; the long pass (which needs ws.x as its transpose buffer) leaves its
+                // column in the plane; then the parked column joins it.  vmask bit ch = channel ch
+                // belongs to the pass.  (A loop, so that each stage has ONE call site.)
+                const int cs = tr0 ? 0 : 1;   // split: the transient channel
                 for (int ps = 0; ps < (kPaired && split ? 2 : 1); ps++) {
-                    const bool is_short = split ? ps == 1 : tr0 != 0;
-                    const int vmask = !(kPaired && split) ? 3 : ((ps == 1) == (tr0 != 0) ? 1 : 2);
-                    const bool pmore = more && (!split || ps == 1);
-                    const int next_nch = kMode == kModeMono ? next_nfr : nch;
-                    if (!is_short) long_frame<kModeT>(p, tb, ws, lane, off, cb, nch, store, pmore, f + nfr, w4, grp, vmask, next_nch);
-                    else short_frame<kModeT>(p, tb, ws, lane, off, cb, nch, store, pmore, f + nfr, grp, vmask, next_nch);
+                    const bool is_short = split ? ps == 0 : tr0 != 0;
+                    const int vmask = !split ? 3 : (is_short ? 1 << cs : 2 >> cs);
+                    stage1_common<kModeT>(tb, ws, lane, is_short, grp);
+                    if (!is_short) {
+                        // every lane has consumed its part of ws.in: the next item's rows can land while stage 2 runs
+                        if (more && !split) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch);
+                        long_stage2<kModeT>(p, ws, lane, off, cb, nch, store, w4, vmask);
+                    } else {
+                        short_stage2<kModeT>(tb, ws, lane, nch, vmask);
+                        if (!split) {
+                            short_output<kModeT>(p, ws, lane, off, cb, nch, store);
+                            if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch);
+                        }
+                    }
+                }
+                if (kPaired && split) {
+                    __syncwarp();
+                    const float *src = ws.in + cs * kInRowFloats;
+                    float *col = reinterpret_cast<float *>(ws.x) + cs;
+                    for (int n = lane; n < kFrame; n += 32) col[2 * n] = src[n];
+                    __syncwarp();
+                    if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch);
                 }
             } else {
                 if (kMode == kModeGroup && grp.pending) {   // see long_frame
@@ -731,12 +726,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                     grp.pending = false;
                 }
                 small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
-                if (more && lane == 0) {   // ws.in fully consumed: prefetch the next frame
-                    const int next_nch = kMode == kModeMono ? next_nfr : nch;
-                    mbar_expect_tx(&ws.bar, next_nch * kFrame * 4);
-                    for (int ch = 0; ch < next_nch; ch++)
-                        tma_load_row(ws.in + ch * kInRowFloats, p.coef + (f + 1) * p.D * kFrame + (cb + ch) * kFrame, kFrame * 4, &ws.bar);
-                }
+                if (more) prefetch_rows(p, ws, lane, f + 1, cb, kMode == kModeMono ? next_nfr : nch);   // ws.in fully consumed
                 const int Nf = kFrame >> sh;
                 if (kMode == kModeGroup) {
                     const int tg = grp.q0;
