@@ -52,7 +52,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def compile_unit(unit):
         src, extra, obj = unit
-        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", os.path.join(objdir, obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *os.environ.get("NQ_EXTRA_NVCC_FLAGS", "").split(), "-c", os.path.join(CSRC, src),
+               "-o", os.path.join(objdir, obj)]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -99,6 +99,10 @@ constexpr int kPlaneOffFloats = 2 * kInRowFloats;   // offsetof(WarpSmem, x) / 4
 #ifndef NQ_PART
 #define NQ_PART 0
 #endif
+#ifndef NQ_SHORT_UNROLL
+#define NQ_SHORT_UNROLL 5
+#endif
+constexpr int kShortUnroll = NQ_SHORT_UNROLL;   // k1 iterations per trip of short_stage2's loop
 
 #if NQ_PART == 0
 size_t fast_kernel_smem_bytes() { return sizeof(FastTables) + kWarpsPerCta * sizeof(WarpSmem); }
@@ -400,11 +404,11 @@ __device__ __forceinline__ void short_stage2(const FastTables &tb, WarpSmem &ws,
     // Y = Z * exp(j 2pi 30 h / 240); y[2k] = -Re Y, y[119-2k] = Im Y with bins k = k1 + 30 h
     //   h = 0: head = y[2k1],    tl = y[119-2k1]
     //   h = 1: head = y[59-2k1], tl = y[60+2k1]
-    const float dr = h ? NQ_SQRT1_2 : 1.0f, di = h ? NQ_SQRT1_2 : 0.0f;
-#pragma unroll 5
+    const float dr = h ? NQ_SQRT1_2 : 1.0f, di = h ? NQ_SQRT1_2 : 0.0f, sg = h ? -1.0f : 1.0f;
+#pragma unroll kShortUnroll
     for (int k1 = 0; k1 < 30; k1++) {
         const float2 a = a_own[k1], pa = a_oth[k1];
-        const float2 z = h ? csub(pa, a) : cadd(a, pa);
+        const float2 z = make_float2(fmaf(sg, a.x, pa.x), fmaf(sg, a.y, pa.y));   // h = 0: a + pa;  h = 1: pa - a
         const float yr = fmaf(z.x, dr, -(z.y * di)), yi = fmaf(z.x, di, z.y * dr);
         const float head = h ? yi : -yr, tl = h ? -yr : yi;
         const int m = h ? 59 - 2 * k1 : 2 * k1;      // head = y[m]
