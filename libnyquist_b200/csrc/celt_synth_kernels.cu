@@ -12,27 +12,32 @@
 //   * one WARP owns a run of consecutive frames of one channel pair and keeps
 //     the 60-sample raw tail on chip between frames (a run that does not
 //     start the batch re-computes the frame before it instead of reading a
-//     tail from memory);
+//     tail from memory); runs are short (64 frames) and, beyond the first
+//     wave, claimed with an atomic so the SMs finish together;
 //   * the frame's two 3840-byte coefficient rows arrive by TMA bulk copy
 //     (cp.async.bulk + mbarrier) into a warp-private shared-memory buffer,
 //     prefetched one frame ahead while the current frame is being computed;
-//   * the 480-point inverse FFT is 30 x 16: stage 1 = 32 lanes x (30-point
-//     prime-factor DFT in registers), one padded, conflict-free shared-memory
-//     transpose, stage 2 = 30 lanes x 2 channels x (16-point DFT in
-//     registers).  The MDCT pre-/post-rotations (incl. the reference's
-//     sin(x)~x factor (1+js)^2) are folded into the single inter-stage
-//     twiddle table plus literal per-slot rotations, so there is one table
-//     load per complex point;
-//   * front/back input pairing and even/odd output pairing are done with one
-//     warp shuffle per point (bins i and N4-1-i live in mirrored lanes);
+//   * the 480-point inverse FFT is 30 x 16, the 60-point one 30 x 2: stage 1
+//     = 32 lanes x (30-point prime-factor DFT in registers) is ONE code path
+//     for long and transient frames (lane-dependent coefficient offsets and
+//     twiddle rows), so the hot code fits the instruction cache whatever
+//     the mix; one padded, conflict-free shared-memory transpose; long stage
+//     2 = 30 lanes x 2 channels x (16-point DFT in registers).  The MDCT
+//     pre-/post-rotations (incl. the reference's sin(x)~x factor (1+js)^2)
+//     are folded into the single inter-stage twiddle table plus literal
+//     per-slot rotations, so there is one table load per complex point;
+//   * even/odd output pairing is done with one warp shuffle per point (bins
+//     k and N4-1-k live in mirrored lanes);
 //   * window, overlap-add and the stereo channel interleave are fused into
 //     the epilogue: each lane stores float4 = {L[n], R[n], L[n+1], R[n+1]},
-//     30 lanes writing 480 contiguous bytes per instruction.
-//   * transient frames (8 short blocks): lanes = (channel, sub-block, half),
-//     60 = 30 x 2, the radix-2 step and the sub-block to sub-block tail are
-//     warp shuffles; output is staged through the transpose buffer so global
-//     stores stay 128-bit and coalesced.
-//   * channel layouts other than plain stereo (mono, 3, 8 channels, Opus
+//     30 lanes writing 480 contiguous bytes per instruction;
+//   * transient frames (8 short blocks): lanes = (channel, sub-block, half);
+//     the radix-2 step reads the partner row of the transpose buffer, the
+//     sub-block to sub-block tail is a warp shuffle, the loop over the 30
+//     bins is rolled; output is parked in the consumed coefficient rows so
+//     global stores stay 128-bit and coalesced;
+//   * a mono stream pairs two consecutive frames as the warp's two channels;
+//   * channel layouts other than plain stereo / mono (3, 8 channels, Opus
 //     multistream with a channel mapping): a GROUP of warps, one per stream,
 //     walks the run in lock-step; each warp leaves its frame as a [960][2]
 //     plane in its (idle) transpose buffer, and after one named barrier the
