@@ -41,7 +41,7 @@ E2E_FRAMES = 262_144                      # host-buffer leg: 2 GB in + 2 GB out 
 FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of celt_synth_kernel<true> from the
 # committed ncu capture (profiles/), scaled to bytes per frame; None until a capture exists.
-NCU_TRAFFIC_BYTES_PER_FRAME = 15483.7    # profiles/r1c_full_stereo10M.csv (the bench's own 10 M-frame launch): (78.043986 + 76.793422) GB / 1e7 frames (64-frame runs: 1/64 of the rows are read twice)
+NCU_TRAFFIC_BYTES_PER_FRAME = 15479.6    # profiles/r1d_full_stereo10M.csv (the bench's own 10 M-frame launch): (78.043522 + 76.752212) GB / 1e7 frames (64-frame runs: 1/64 of the rows are read twice)
 
 
 # Only the JSON line may reach stdout: NCCL (and anything else that writes to the C-level stdout,
