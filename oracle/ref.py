@@ -49,6 +49,7 @@ def lib():
         L.nqref_last_layout.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
         L.nqref_encode_surround.argtypes = [fp, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_long]
         L.nqref_encode_surround.restype = C.c_long
+        L.nqref_patch_output_gain.argtypes = [C.c_void_p, C.c_long, C.c_int]
         L.nqref_comb_filter.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
         L.nqref_deemphasis.argtypes = [C.POINTER(fp), fp, C.c_int, C.c_int, fp]
         _lib = L
@@ -188,6 +189,15 @@ def encode_surround(pcm: np.ndarray, bitrate: int = 512000) -> bytes:
     if got < 0:
         raise RuntimeError(f"reference encoder failed: {got}")
     return out[:got].tobytes()
+
+
+def with_output_gain(data: bytes, gain_q8: int) -> bytes:
+    """The same Ogg Opus file with OpusHead.output_gain (Q7.8 dB) rewritten and the page CRC fixed."""
+    a = np.frombuffer(data, np.uint8).copy()
+    rc = lib().nqref_patch_output_gain(a.ctypes.data_as(C.c_void_p), a.size, int(gain_q8))
+    if rc != 0:
+        raise RuntimeError(f"not an Ogg Opus file ({rc})")
+    return a.tobytes()
 
 
 def comb_filter(buf: np.ndarray, start: int, T0, T1, N, g0, g1, tapset0, tapset1) -> None:

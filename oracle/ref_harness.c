@@ -411,6 +411,26 @@ NQREF_API long nqref_encode_surround(const float *pcm, long nsamples, int channe
     return pos;
 }
 
+/* Rewrites the output-gain field (Q7.8 dB, RFC 7845 section 5.1) of an in-memory Ogg Opus file's
+ * OpusHead and fixes the page checksum, so the header-gain path (opusfile OP_HEADER_GAIN ->
+ * OPUS_SET_GAIN -> opus_decoder_clean.c:578-588) can be exercised on the bundled files. */
+NQREF_API int nqref_patch_output_gain(unsigned char *data, long nbytes, int gain_q8)
+{
+    ogg_page og;
+    long i, body_len = 0;
+    int nsegs;
+    if (nbytes < 47 || memcmp(data, "OggS", 4) != 0) return -1;
+    nsegs = data[26];
+    for (i = 0; i < nsegs; i++) body_len += data[27 + i];
+    if (27 + nsegs + body_len > nbytes || body_len < 19 || memcmp(data + 27 + nsegs, "OpusHead", 8) != 0) return -2;
+    data[27 + nsegs + 16] = (unsigned char)(gain_q8 & 255);
+    data[27 + nsegs + 17] = (unsigned char)((gain_q8 >> 8) & 255);
+    og.header = data; og.header_len = 27 + nsegs;
+    og.body = data + 27 + nsegs; og.body_len = body_len;
+    ogg_page_checksum_set(&og);
+    return 0;
+}
+
 NQREF_API long nqref_record_count(void) { return g_rec.nrecords; }
 NQREF_API size_t nqref_record_floats(void) { return g_rec.len; }
 NQREF_API void nqref_record_copy(float *dst) { memcpy(dst, g_rec.buf, g_rec.len * sizeof(float)); }

@@ -96,6 +96,38 @@ def test_nyquistio_load_two_phase_8_channel_multistream(twophase):
           f"vs reference Load {t_ref * 1e3:.0f} ms; max |err| {err:.2e}")
 
 
+@pytest.mark.parametrize("gain_q8", [-1536, 768])
+def test_header_gain_is_applied_like_the_reference(twophase, tmp_path, gain_q8):
+    """OpusHead.output_gain (opusfile OP_HEADER_GAIN -> OPUS_SET_GAIN -> opus_decoder_clean.c:578-588):
+    short.opus with the gain field rewritten to -6 dB / +3 dB."""
+    src = os.path.join(os.path.dirname(ref.LIB_PATH), "test_data", "short.opus")
+    if not (ref.available() and os.path.exists(src)):
+        pytest.skip("oracle/_ref (compiled reference + staged test_data) not present")
+    path = tmp_path / "gain.opus"
+    path.write_bytes(ref.with_output_gain(open(src, "rb").read(), gain_q8))
+    got, ch, sr, tm, wall = load(twophase, str(path))
+    want, _ = ref.decode_file(str(path))
+    plain, _ = ref.decode_file(src)
+    assert ref.header_info()[1] == 0 and got is not None and got.shape == want.shape
+    scale = float(np.abs(want).max() / np.abs(plain).max())
+    assert abs(scale - 10 ** (gain_q8 / 256 / 20)) < 1e-4          # the reference really applied it
+    assert float(np.abs(got.astype(np.float64) - want).max()) <= 1e-5 * max(1.0, scale)
+    assert snr_db(want, got) >= 100.0
+
+
+def test_silk_file_is_refused_not_misdecoded(twophase):
+    """The two-phase build covers CELT-only streams.  test_data/ad_hoc/detodos.opus is SILK: Load
+    must fail loudly (the overlay notes silk_Decode), never return audio without the SILK part."""
+    path = os.path.join(os.path.dirname(ref.LIB_PATH), "test_data", "detodos.opus")
+    if not os.path.exists(path):
+        pytest.skip("detodos.opus not staged")
+    got, *_ = load(twophase, path)
+    assert got is None
+    if ref.available():
+        want, _ = ref.decode_file(path)
+        assert want.shape == (139848, 1)                                # the reference itself decodes it
+
+
 def test_two_phase_load_errors_like_the_reference(twophase, tmp_path):
     bad = tmp_path / "noise.opus"
     bad.write_bytes(np.random.default_rng(0).integers(0, 256, 5000, dtype=np.uint8).tobytes())
