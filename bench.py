@@ -481,7 +481,10 @@ def main():
     if not args.no_extras and world == 1:
         del coef, pcm
         torch.cuda.empty_cache()
-        line["extras"] = extras(torch, np, nq, synth, dev, peak, not args.no_cpu_baseline)
+        try:   # informational legs: they must never cost the bench line
+            line["extras"] = extras(torch, np, nq, synth, dev, peak, not args.no_cpu_baseline)
+        except Exception as e:
+            line["extras_error"] = repr(e)
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
