@@ -30,7 +30,7 @@ class WarpModel:
         i = 16 * n1[None, :] + n2[:, None]
         vx = rows[c1[:, None], 2 * i]
         vy = rows[c1[:, None], 2 * i + 1]
-        # xb = shfl_xor(v[29-n1].y, 15)
+        # xb = X[959 - 2i]: the odd element of bin 479-i, i.e. lane^15's v[29-n1].y (the kernel reads it directly)
         xb = vy[lanes ^ 15][:, ::-1]
         g = (xb + 1j * vx) * self.pre[None, :]
         A = _idft(g, 1)                                    # [lane][k1]

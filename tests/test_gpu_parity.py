@@ -305,6 +305,18 @@ def test_multistream_batch_with_short_frames(synth):
     assert_parity(want, pcm.cpu().numpy(), "7.1 any-size")
 
 
+def test_more_channel_pairs_than_warps_direct_variant(synth):
+    """30 plain channels = 15 pairs, one more than a CTA has warps: the scattered-store variant."""
+    assert nq.debug_plan(30)["mode"] == nq.MODE_DIRECT
+    rng = np.random.default_rng(30)
+    coef, tr = rand_batch(rng, 300, 30, 0.2)
+    tail_in = (rng.standard_normal((30, 60)) * 100).astype(np.float32)
+    want, want_tail, _ = port.synth_batch(coef, tr, tail_in, nthreads=8)
+    pcm, tail = synth.synth_batch(coef, tr, tail_in)
+    assert_parity(want, pcm, "C 30")
+    assert_parity(want_tail, tail, "tail")
+
+
 def test_edge_cases_and_error_codes(synth):
     rng = np.random.default_rng(5)
     # empty batch: tail passes through
