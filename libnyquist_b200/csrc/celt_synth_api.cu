@@ -237,7 +237,7 @@ int plan_layout(const Layout &L, int num_sms, long long nframes, SynthParams *pp
             const int d = L.mapping[c];
             vec = d != 255 && d < 2 * L.coupled && (d & 1) == 0 && L.mapping[c + 1] == d + 1;
         }
-        p.store_shape = muted ? 2 : (vec ? 0 : 1);
+        p.store_shape = p.store_threads == 0 ? 3 : (muted ? 2 : (vec ? 0 : 1));
         for (int c = 0; c < L.C; c++) {
             const int d = L.mapping[c];
             if (d == 255) p.chan_src[c] = 0xffffu;   // muted channel, opus_multistream_decoder.c:291-299

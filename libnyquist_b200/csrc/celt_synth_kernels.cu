@@ -123,6 +123,7 @@ struct GroupCtx {
     uint32_t step;         // byte advance per iteration: (4*T2/C) samples * 8 bytes (planes are [960][2])
     int q0, T2, niter;     // first float4, stride, iterations (0 for the threads beyond T2)
     int T, bar_id;         // threads in the group, its named barrier (1..15)
+    uint32_t planes;       // shared-memory byte address of the group's first plane
     unsigned mute;         // bit j: element j belongs to a silent output channel
     int shape;             // store-loop shape, see group_store_frame (uniform over the group)
     bool pending;          // the previous frame's store pass may still be reading the planes
@@ -152,6 +153,26 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
 // shapes, chosen once per kernel: both element pairs of a thread are the two channels of one
 // coupled stream in order (plain layouts: 2 x LDS.64), the general gather (4 x LDS.32), and the
 // general gather with silent channels.
+// General form (shape 3), for channel counts no store-thread count divides evenly (4*T2 % C != 0 for
+// every usable T2: many duplicated output channels on few streams): every float4 of the output frame
+// is gathered element by element, channel and sample re-derived per element.  Slow, correct, rare.
+static __device__ __noinline__ void group_store_frame_general(const SynthParams &p, uint32_t planes, int tg, int T, float *frame_out, int nsamples)
+{
+    const int C = p.C, nq4 = (nsamples / 4) * C;
+    float4 *dst = reinterpret_cast<float4 *>(frame_out);
+    for (int q = tg; q < nq4; q += T) {
+        int n = (4 * q) / C, c = (4 * q) % C;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned sc = p.chan_src[c];
+            v[j] = sc == 0xffffu ? 0.f : lds_f32(planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + (sc & 1) * 4 + n * 8);
+            if (++c == C) { c = 0; n++; }
+        }
+        __stcs(dst + q, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
 __device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *frame_out, int niter)
 {
     float4 *dst = reinterpret_cast<float4 *>(frame_out) + g.q0;
@@ -600,7 +621,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         const int tg = slot * 32 + lane, C = p.C;
         grp.T = W * 32;
         grp.bar_id = 1 + gi;
-        grp.T2 = p.store_threads;
+        grp.T2 = p.store_threads > 0 ? p.store_threads : 1;   // store_threads == 0: general store loop (shape 3)
         grp.q0 = tg;
         grp.step = (uint32_t)(4 * grp.T2 / C) * 8u;
         grp.niter = tg < grp.T2 ? ((kFrame / 4) * C - tg + grp.T2 - 1) / grp.T2 : 0;
@@ -614,6 +635,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             grp.src[j] = sc == 0xffffu ? planes : planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + (sc & 1) * 4 + n * 8;
             if (++c == C) { c = 0; n++; }
         }
+        grp.planes = planes;
         grp.shape = p.store_shape;
         item = (long long)blockIdx.x * G + gi;
         item_stride = (long long)gridDim.x * G;
@@ -758,7 +780,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             }
             if (kMode == kModeGroup && store) {
                 group_sync(grp);   // every stream's plane of frame f is complete
-                group_store_frame(grp, p.pcm + off * p.C, niter);
+                if (grp.shape == 3) group_store_frame_general(p, grp.planes, grp.q0, grp.T, p.pcm + off * p.C, kFrame >> sh);
+                else group_store_frame(grp, p.pcm + off * p.C, niter);
                 grp.pending = true;   // ... and must stay intact until the whole group is through this pass
             }
             flag = next_flag;
@@ -869,7 +892,7 @@ int synth_mode(int D, int C, int nstreams, bool identity_map, bool one_decoder)
 {
     if (D == 2 && C == 2 && nstreams == 1 && identity_map && one_decoder) return kModeStereo;
     if (D == 1 && C == 1 && identity_map) return kModeMono;
-    if (nstreams <= kMaxGroupStreams && group_store_threads(C, nstreams) > 0) return kModeGroup;
+    if (nstreams <= kMaxGroupStreams) return kModeGroup;   // (store pass: group_store_threads() or the general loop)
     return kModeDirect;
 }
 

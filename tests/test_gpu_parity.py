@@ -190,6 +190,8 @@ MS_LAYOUTS = {
     "dual_mono_identity": (2, 0, [0, 1]),      # D = C = 2 like stereo, but two decoders with their own flags
     "five_mono_odd": (5, 0, [4, 3, 2, 1, 0]),
     "max_warps_13_coupled_2_mono": (15, 13, list(range(28))),
+    # 37 output channels fed by 3 decoded ones: no store-thread count divides evenly -> general store loop
+    "thirty_seven_outputs_one_stream": (1, 1, [(7 * i) % 2 if i % 5 else 255 for i in range(37)]),
 }
 
 

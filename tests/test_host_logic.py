@@ -163,6 +163,8 @@ def test_plan_multistream_layouts():
     assert (dual["mode"], dual["warps_per_group"], dual["paired_mono"]) == (nq.MODE_GROUP, 1, 1)
     seven = nq.debug_plan(14, 7, 7, list(range(14)))
     assert (seven["warps_per_group"], seven["groups_per_cta"]) == (7, 2)   # the 14-warp variant
+    odd = nq.debug_plan(37, 1, 1, [(7 * i) % 2 if i % 5 else 255 for i in range(37)])
+    assert (odd["mode"], odd["store_threads"], odd["store_shape"]) == (nq.MODE_GROUP, 0, 3)   # general store loop
     with pytest.raises(nq.NqError) as e:
         nq.debug_plan(29, 29, 0, list(range(29)))                      # 15 warps: one more than a CTA has
     assert e.value.code == -5
