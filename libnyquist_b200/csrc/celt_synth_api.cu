@@ -215,6 +215,9 @@ int plan_layout(const Layout &L, int num_sms, long long nframes, SynthParams *pp
     long long resident = (long long)num_sms * kWarpsPerCta / p.npairs;
     if (mode == kModeGroup) {
         resident = (long long)num_sms * groups_per_cta(nslots);
+        p.groups_per_cta = groups_per_cta(nslots);
+        p.store_warps = group_store_warps(nslots);
+        p.store_warps_cta = group_store_warps_cta(nslots);
         p.store_threads = group_store_threads(L.C, nslots);
         for (int s = 0; s < L.coupled; s++) {
             p.streams[s].nch = 2;

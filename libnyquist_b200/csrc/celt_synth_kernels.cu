@@ -74,6 +74,26 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t 
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long *bar, uint32_t parity)   // non-blocking
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
 __device__ __forceinline__ void tma_load_row(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
 {
@@ -90,7 +110,13 @@ struct __align__(16) WarpSmem {
     float2 x[2 * kXChanF2];           // inter-stage transpose buffer / short-frame output staging
     float tail[2 * kHalfOvl];         // raw tail y[N2-60..N2) of the previous (sub-)block, per channel
     unsigned long long bar;           // mbarrier for the TMA prefetch
+    // Group mode, used in the WarpSmem of the group's first warp only: the hand-over between the
+    // group's synthesis warps and its store warp(s), and the ring through which the group's first
+    // warp publishes the runs it claims.
+    unsigned long long full;          // mbarrier: every synthesis warp's plane of the frame is complete
+    unsigned long long empty;         // mbarrier: the store warps are done reading the planes
     unsigned long long pad_;
+    unsigned long long claim[4];      // (run << 8 | sequence number), see celt_synth_kernel
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp smem slice must keep 16-byte alignment");
 static_assert((kInRowFloats * 4) % 16 == 0, "TMA destination rows must be 16-byte aligned");
@@ -113,26 +139,41 @@ constexpr int kShortUnroll = NQ_SHORT_UNROLL;   // k1 iterations per trip of sho
 size_t fast_kernel_smem_bytes() { return sizeof(FastTables) + kWarpsPerCta * sizeof(WarpSmem); }
 #endif
 
-// Group mode: the warps of one group (one per stream) and their cooperative store pass.
-// The output frame [960][C] is written as 240*C float4; thread tg of the first T2 threads
-// of the group owns float4 q = tg + T2*i.  T2 is chosen on the host so that 4*T2 is a multiple
-// of C: the four output channels a thread serves are then the same in every iteration, and
-// only the sample index advances (by 4*T2/C).
-struct GroupCtx {
+// Group mode is warp-specialised: the group's SYNTHESIS warps (one per stream) each leave their
+// frame as a [960][2] plane in shared memory and arrive on the group's `full` mbarrier; the group's
+// STORE warp(s) wait for it, write the interleaved [960][C] output frame and arrive on `empty`,
+// which a synthesis warp waits for only when it is about to overwrite its plane (after stage 1's
+// loads and 30-point transforms of the next frame).  The synthesis warps therefore never wait for
+// each other, carry none of the store pass's state or code, and run one frame ahead of the store.
+//
+// Store pass: the output frame is 240*C float4; thread tg of the first T2 store threads owns float4
+// q = tg + T2*i.  T2 is chosen on the host so that 4*T2 is a multiple of C: the four output channels
+// a thread serves are then the same in every iteration, and only the sample index advances (by
+// 4*T2/C).
+struct StoreCtx {
     uint32_t src[4];       // shared-memory byte address of this thread's four elements at iteration 0
     uint32_t step;         // byte advance per iteration: (4*T2/C) samples * 8 bytes (planes are [960][2])
-    int q0, T2, niter;     // first float4, stride, iterations (0 for the threads beyond T2)
-    int T, bar_id;         // threads in the group, its named barrier (1..15)
+    int q0, T2, niter;     // first float4, stride, iterations for a 20 ms frame (0 for the threads beyond T2)
+    int T;                 // store threads of the group
     uint32_t planes;       // shared-memory byte address of the group's first plane
     unsigned mute;         // bit j: element j belongs to a silent output channel
     int shape;             // store-loop shape, see group_store_frame (uniform over the group)
-    bool pending;          // the previous frame's store pass may still be reading the planes
 };
 
-__device__ __forceinline__ void group_sync(const GroupCtx &g)
+// A synthesis warp's view of its group.
+struct GroupLink {
+    unsigned long long *full, *empty;
+    uint32_t nstored;      // frames handed to the store warps so far
+    bool pending;          // the store pass of the last one may still be reading this warp's plane
+};
+
+// Called before anything is written to ws.x (the plane of the previous stored frame).
+__device__ __forceinline__ void group_wait_plane_free(GroupLink &g)
 {
-    if (g.T == 32) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "r"(g.T) : "memory");
+    if (g.pending) {
+        mbar_wait(g.empty, (g.nstored - 1) & 1);
+        g.pending = false;
+    }
 }
 
 __device__ __forceinline__ float lds_f32(uint32_t addr)
@@ -173,10 +214,10 @@ static __device__ __noinline__ void group_store_frame_general(const SynthParams 
     }
 }
 
-__device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *frame_out, int niter)
+__device__ __forceinline__ void group_store_frame(const StoreCtx &g, uint32_t base, float *frame_out, int niter)
 {
     float4 *dst = reinterpret_cast<float4 *>(frame_out) + g.q0;
-    uint32_t a0 = g.src[0], a1 = g.src[1], a2 = g.src[2], a3 = g.src[3];
+    uint32_t a0 = base + g.src[0], a1 = base + g.src[1], a2 = base + g.src[2], a3 = base + g.src[3];
     const uint32_t step = g.step;
     const int T2 = g.T2;
     if (g.shape == 0) {
@@ -214,11 +255,10 @@ __device__ __forceinline__ void group_store_frame(const GroupCtx &g, float *fram
 __device__ __forceinline__ void prefetch_rows(const SynthParams &p, WarpSmem &ws, int lane, long long fnext, int cb, int rows)
 {
     if (lane == 0) {
+        const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + cb * kFrame;
         mbar_expect_tx(&ws.bar, rows * kFrame * 4);
-        for (int ch = 0; ch < rows; ch++) {
-            const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + (cb + ch) * kFrame;
-            tma_load_row(ws.in + ch * kInRowFloats, src, kFrame * 4, &ws.bar);
-        }
+        tma_load_row(ws.in, src, kFrame * 4, &ws.bar);
+        if (rows == 2) tma_load_row(ws.in + kInRowFloats, src + kFrame, kFrame * 4, &ws.bar);
     }
 }
 
@@ -234,7 +274,7 @@ __device__ __forceinline__ void prefetch_rows(const SynthParams &p, WarpSmem &ws
 // multiply by a lane-dependent row of a twiddle table (rotations + inter-stage twiddle folded, DESIGN.md
 // section 3); the products go to the transpose buffer ws.x[c][r][k1].
 template <int kModeT>
-__device__ __forceinline__ void stage1_common(const FastTables &tb, WarpSmem &ws, int lane, bool is_short, GroupCtx &grp)
+__device__ __forceinline__ void stage1_common(const FastTables &tb, WarpSmem &ws, int lane, bool is_short, GroupLink &grp)
 {
     constexpr int kMode = kModeT == kModeGroupPaired ? kModeGroup : kModeT;
     constexpr float pre_re[30] = {NQ_PRE30_RE};
@@ -250,10 +290,7 @@ __device__ __forceinline__ void stage1_common(const FastTables &tb, WarpSmem &ws
         g[n1] = make_float2(fmaf(xb, pre_re[n1], -(xa * pre_im[n1])), fmaf(xb, pre_im[n1], xa * pre_re[n1]));
     }
     idft30(g);
-    if (kMode == kModeGroup && grp.pending) {   // the group's previous store pass reads ws.x of every warp
-        group_sync(grp);
-        grp.pending = false;
-    }
+    if (kMode == kModeGroup) group_wait_plane_free(grp);   // the store pass of the previous frame reads ws.x
     const float2 *tw = is_short ? tb.t_short + h * 30 : tb.t_long + r * kXRowF2;
     float2 *dst = ws.x + c * kXChanF2 + r * kXRowF2;
 #pragma unroll
@@ -563,10 +600,107 @@ static __device__ __noinline__ void small_frame_planes(const GenericTables *gt, 
     }
 }
 
+// ------------------------------------------------ group mode: store warps ---
+// Next run of a group.  Static: item + stride.  Dynamic: the group's first synthesis warp claims the
+// run after next with an atomic when it STARTS a run and publishes it, tagged with the run's
+// sequence number, in a ring of four words in shared memory; everybody else in the group (the other
+// synthesis warps, the store warps) polls that word when it FINISHES the run.  (The warps of a group
+// are never more than two frames apart, so a ring of four cannot be overrun; a sequence tag rather
+// than an mbarrier because the claimer may be a phase ahead of a reader.)
+__device__ __forceinline__ long long group_next_item(const volatile unsigned long long *claim, unsigned seq)
+{
+    unsigned long long w;
+    do w = claim[seq & 3]; while ((unsigned)(w & 0xff) != (seq & 0xff));
+    return (long long)(w >> 8);
+}
+
+// One store warp.  A group's frame is stored by SW store warps ("units" (group, part)); a CTA has
+// NS store warps, and store warp s serves the units s, s + NS, ... (one unit each except in the
+// layouts with many narrow groups): it polls their `full` barriers, writes the unit's part of the
+// interleaved frame and releases the planes.  Every unit walks the same runs and frames as the
+// synthesis warps of its group.
+constexpr int kMaxStoreUnits = 3;   // 12 groups of one synthesis warp over 4 store warps
+
+template <bool kAnySize>
+__device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem *wsmem, int s, int lane)
+{
+    const int C = p.C, W = p.nstreams, G = p.groups_per_cta, SW = p.store_warps, NS = p.store_warps_cta;
+    const int tg = (s % SW) * 32 + lane;   // (NS is a multiple of SW: every unit of this warp is the same part)
+    StoreCtx st;
+    st.T = SW * 32;
+    st.T2 = p.store_threads > 0 ? p.store_threads : 1;   // store_threads == 0: general store loop (shape 3)
+    st.q0 = tg;
+    st.step = (uint32_t)(4 * st.T2 / C) * 8u;
+    st.niter = tg < st.T2 ? ((kFrame / 4) * C - tg + st.T2 - 1) / st.T2 : 0;
+    st.mute = 0;
+    st.planes = kPlaneOffFloats * 4;   // relative to the group's first slice
+    st.shape = p.store_shape;
+    {
+        int n = (4 * tg) / C, c = (4 * tg) % C;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned sc = p.chan_src[c];
+            if (sc == 0xffffu) st.mute |= 1u << j;
+            st.src[j] = sc == 0xffffu ? st.planes : st.planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + (sc & 1) * 4 + n * 8;
+            if (++c == C) { c = 0; n++; }
+        }
+    }
+    const bool dynamic = p.work_counter != nullptr;
+    const long long item_stride = (long long)gridDim.x * G;
+    long long item[kMaxStoreUnits] = {}, f[kMaxStoreUnits] = {}, f1[kMaxStoreUnits] = {};
+    uint32_t nstored[kMaxStoreUnits] = {}, seq[kMaxStoreUnits] = {};
+    WarpSmem *ugws[kMaxStoreUnits] = {};
+    int nunits = 0, alive = 0;
+    auto start_run = [&](int k) {
+        if (item[k] < p.nruns) {
+            seq[k]++;
+            f[k] = item[k] * p.frames_per_run;
+            f1[k] = (f[k] + p.frames_per_run < p.nframes) ? f[k] + p.frames_per_run : p.nframes;
+        } else {
+            f[k] = f1[k] = 0;
+            alive--;
+        }
+    };
+    for (int u = s; u < G * SW && nunits < kMaxStoreUnits; u += NS, nunits++) {
+        item[nunits] = (long long)blockIdx.x * G + u / SW;
+        ugws[nunits] = wsmem + (u / SW) * W;
+        alive++;
+        start_run(nunits);
+    }
+    while (alive > 0) {
+        bool any = false;
+        for (int k = 0; k < nunits; k++) {
+            if (f[k] >= f1[k]) continue;
+            WarpSmem *gws = ugws[k];
+            if (nunits == 1) mbar_wait(&gws->full, nstored[k] & 1);
+            else if (!mbar_test_wait(&gws->full, nstored[k] & 1)) continue;
+            any = true;
+            const long long fr = f[k];
+            int niter = st.niter, nsamples = kFrame;
+            float *out = p.pcm + fr * kFrame * C;
+            if (kAnySize) {   // (every stream of a frame carries the same size bits)
+                const int sh = (p.transient[fr * p.flag_stride] >> 1) & 3;
+                nsamples = kFrame >> sh;
+                niter = tg < st.T2 ? ((nsamples / 4) * C - tg + st.T2 - 1) / st.T2 : 0;
+                out = p.pcm + p.frame_offset[fr] * C;
+            }
+            const uint32_t base = smem_u32(gws);
+            if (st.shape == 3) group_store_frame_general(p, base + st.planes, st.q0, st.T, out, nsamples);
+            else group_store_frame(st, base, out, niter);
+            mbar_arrive(&gws->empty);   // (release: this thread's reads of the planes are done)
+            nstored[k]++;
+            if (++f[k] == f1[k]) {
+                item[k] = dynamic ? group_next_item(gws->claim, seq[k]) : item[k] + item_stride;
+                start_run(k);
+            }
+        }
+        if (!any) __nanosleep(100);   // several units, none ready: leave the issue slots to the synthesis warps
+    }
+}
+
 // ----------------------------------------------------------- fast kernel ---
-// kWarps = warps per CTA: 14 (what shared memory allows), or 12 for group shapes that cannot use
-// more than 12 anyway -- three warps per scheduler instead of four lifts the register cap from
-// 128 to 168 per thread, which the group variant needs to stay out of local memory.
+// kWarps: stereo / mono / direct: 14 warps per CTA (what shared memory allows).  Group: up to 16
+// (G*W synthesis warps followed by the CTA's store warps), 128 registers each like the others.
 // kAnySize: the batch may hold frames shorter than 20 ms (p.frame_offset != nullptr).  A separate
 // instantiation, so that the common all-20-ms kernel keeps its register allocation.
 template <int kModeT, int kWarps, bool kAnySize>
@@ -582,20 +716,47 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
     FastTables &tb = *reinterpret_cast<FastTables *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem *wsmem = reinterpret_cast<WarpSmem *>(smem_raw + sizeof(FastTables));
-    WarpSmem &ws = wsmem[warp];
+
+    // Roles.  Stereo / mono / direct: every warp synthesises.  Group: warps [0, G*W) synthesise
+    // (group gi = warp / W, stream slot = warp % W), the next G*SW warps store.
+    int gi = 0, slot = 0, store_warp = -1;
+    const int W = kMode == kModeGroup ? p.nstreams : 1, G = kMode == kModeGroup ? p.groups_per_cta : 0;
+    if (kMode == kModeGroup) {
+        if (warp < G * W) {
+            gi = warp / W;
+            slot = warp - gi * W;
+        } else {
+            store_warp = warp - G * W;
+        }
+    }
+    const bool synth_warp = store_warp < 0;
+    WarpSmem &ws = wsmem[synth_warp ? warp : 0];   // (only synthesis warps have a slice of their own)
+    WarpSmem *gws = wsmem + gi * W;                 // group mode: the group's first slice holds its barriers
 
     {
         const float *src = reinterpret_cast<const float *>(p.tables);
         float *dst = reinterpret_cast<float *>(&tb);
         for (int i = threadIdx.x; i < int(sizeof(FastTables) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    for (int i = lane; i < 2 * kInRowFloats; i += 32) ws.in[i] = 0.f;
-    if (lane == 0) {
-        mbar_init(&ws.bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (synth_warp) {
+        for (int i = lane; i < 2 * kInRowFloats; i += 32) ws.in[i] = 0.f;
+        if (lane == 0) {
+            mbar_init(&ws.bar, 1);
+            if (kMode == kModeGroup && slot == 0) {
+                mbar_init(&ws.full, 32 * W);
+                mbar_init(&ws.empty, 32 * p.store_warps);
+                for (int i = 0; i < 4; i++) ws.claim[i] = 0;
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    if (kMode == kModeGroup && !synth_warp) {   // (no block-wide barrier below this point)
+        group_store_role<kAnySize>(p, wsmem, store_warp, lane);
+        return;
+    }
 
     // lane-constant window taps of the long-block mirror: k1 = lane (< 30)
     float w4[4];
@@ -607,36 +768,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         w4[3] = tb.window[61 + 2 * k1];
     }
 
-    // Work items.  Stereo / direct: one warp per (run, channel pair).  Group: the CTA holds
-    // kWarpsPerCta / nstreams groups, a group owns a run, warp `slot` of the group owns stream `slot`.
+    // Work items.  Stereo / direct: one warp per (run, channel pair).  Group: a group owns a run,
+    // synthesis warp `slot` of the group owns stream `slot`.
     long long item, item_stride, nitems;
-    int slot = 0;
-    GroupCtx grp;
+    GroupLink grp;
+    grp.full = &gws->full;
+    grp.empty = &gws->empty;
+    grp.nstored = 0;
     grp.pending = false;
+    uint32_t seq = 0;               // group mode: runs started so far
+    long long claimed = 0;          // group mode, first warp: the run after this one
     if (kMode == kModeGroup) {
-        const int W = p.nstreams, G = kWarps / W;
-        const int gi = warp / W;
-        slot = warp - gi * W;
-        if (gi >= G) return;   // spare warps (no block-wide barrier below this point)
-        const int tg = slot * 32 + lane, C = p.C;
-        grp.T = W * 32;
-        grp.bar_id = 1 + gi;
-        grp.T2 = p.store_threads > 0 ? p.store_threads : 1;   // store_threads == 0: general store loop (shape 3)
-        grp.q0 = tg;
-        grp.step = (uint32_t)(4 * grp.T2 / C) * 8u;
-        grp.niter = tg < grp.T2 ? ((kFrame / 4) * C - tg + grp.T2 - 1) / grp.T2 : 0;
-        grp.mute = 0;
-        int n = (4 * tg) / C, c = (4 * tg) % C;
-        const uint32_t planes = smem_u32(wsmem + gi * W) + kPlaneOffFloats * 4;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const unsigned sc = p.chan_src[c];
-            if (sc == 0xffffu) grp.mute |= 1u << j;
-            grp.src[j] = sc == 0xffffu ? planes : planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + (sc & 1) * 4 + n * 8;
-            if (++c == C) { c = 0; n++; }
-        }
-        grp.planes = planes;
-        grp.shape = p.store_shape;
         item = (long long)blockIdx.x * G + gi;
         item_stride = (long long)gridDim.x * G;
         nitems = p.nruns;
@@ -653,12 +795,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
     uint32_t phase = 0;
     for (; item < nitems;) {
         long long run;
-        int cb, nch, flag_col, halo_bit, flag_col1 = -1;
+        int cb, nch, rows, flag_col, halo_bit, flag_col1 = -1;
         if (kMode == kModeGroup) {
+            if (dynamic) {   // see group_next_item
+                seq++;
+                if (slot == 0) {
+                    unsigned long long next = 0;
+                    if (lane == 0) {
+                        next = atomicAdd(p.work_counter, 1ULL) + (unsigned long long)item_stride;
+                        if (next > (unsigned long long)nitems) next = (unsigned long long)nitems;
+                        *reinterpret_cast<volatile unsigned long long *>(&gws->claim[seq & 3]) = next << 8 | (seq & 0xff);
+                    }
+                    claimed = (long long)__shfl_sync(kFull, next, 0);
+                }
+            }
             const StreamDesc sd = p.streams[slot];
             run = item;
             cb = sd.row;
-            nch = sd.nch;
+            // A group's warp always computes two channels (a compile-time width keeps the stage
+            // functions inside the register budget): a lone mono stream's second channel has no
+            // coefficient row -- its buffer stays zero -- and no reader.
+            rows = sd.nch;
+            nch = 2;
             flag_col = sd.flag_col;
             halo_bit = sd.flag_col;
             if (kPaired && sd.flag_col1 != sd.flag_col) flag_col1 = sd.flag_col1;   // two mono streams in one warp
@@ -666,7 +824,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             run = kStereo ? item : item / p.npairs;
             const int pair = kStereo ? 0 : int(item - run * p.npairs);
             cb = 2 * pair;
-            nch = kStereo ? 2 : (p.D - cb >= 2 ? 2 : 1);
+            rows = nch = kStereo ? 2 : (p.D - cb >= 2 ? 2 : 1);
             flag_col = p.flag_per_stream ? pair : 0;
             halo_bit = p.flag_per_stream ? (pair & 31) : 0;
         }
@@ -680,7 +838,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         for (int i = lane; i < 2 * kHalfOvl; i += 32) {
             const int ch = i / kHalfOvl;
             float t = 0.f;
-            if (!warm && p.tail_in != nullptr && ch < nch) t = p.tail_in[(cb + ch) * kHalfOvl + (i - ch * kHalfOvl)];
+            if (!warm && p.tail_in != nullptr && ch < rows) t = p.tail_in[(cb + ch) * kHalfOvl + (i - ch * kHalfOvl)];
             ws.tail[i] = t;
         }
         __syncwarp();
@@ -698,8 +856,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             return kMode == kModeMono && g >= f0 && g + 1 < f1 && (gflag >> 1) == 0 && flags[(g + 1) * p.flag_stride] == gflag;
         };
         int nfr = (kMode == kModeMono && mono_pair(f, flag)) ? 2 : 1;
-        const int state_nch = nch;   // channels with a tail of their own (kModeMono: nch is reused as frames per item)
-        prefetch_rows(p, ws, lane, f, cb, kMode == kModeMono ? nfr : nch);
+        const int state_nch = rows;   // channels with a tail of their own (kModeMono: nch is reused as frames per item)
+        prefetch_rows(p, ws, lane, f, cb, kMode == kModeMono ? nfr : rows);
         while (f < f1) {
             if (kMode == kModeMono) nch = nfr;
             const bool more = f + nfr < f1;
@@ -716,11 +874,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             const bool store = f >= f0;
             const long long off = (kAnySize && store) ? p.frame_offset[f] : f * kFrame;
             const int sh = kAnySize ? (flag >> 1) & 3 : 0;   // (bits above 2 are not part of the size)
-            int niter = grp.niter;
             const int tr0 = flag & 1;
             const bool split = kPaired && tr1 >= 0 && tr1 != tr0;
             if (sh == 0) {
-                const int next_nch = kMode == kModeMono ? next_nfr : nch;
+                const int next_nch = kMode == kModeMono ? next_nfr : rows;
                 // One pass -- or, for two mono streams in one warp that disagree about block switching,
                 // two: the short pass goes first and parks its channel's samples in that channel's own
                 // coefficient row; the long pass (which needs ws.x as its transpose buffer) leaves its
@@ -752,17 +909,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                     if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch);
                 }
             } else {
-                if (kMode == kModeGroup && grp.pending) {   // see long_frame
-                    group_sync(grp);
-                    grp.pending = false;
-                }
-                small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
-                if (more) prefetch_rows(p, ws, lane, f + 1, cb, kMode == kModeMono ? next_nfr : nch);   // ws.in fully consumed
+                if (kMode == kModeGroup) group_wait_plane_free(grp);
+                small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, kMode == kModeGroup ? rows : nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
+                if (more) prefetch_rows(p, ws, lane, f + 1, cb, kMode == kModeMono ? next_nfr : rows);   // ws.in fully consumed
                 const int Nf = kFrame >> sh;
-                if (kMode == kModeGroup) {
-                    const int tg = grp.q0;
-                    niter = tg < grp.T2 ? ((Nf / 4) * p.C - tg + grp.T2 - 1) / grp.T2 : 0;
-                } else if (store) {
+                if (kMode != kModeGroup && store) {
                     const float *plane = reinterpret_cast<const float *>(ws.x);
                     if (kStereo) {
                         const float4 *s4 = reinterpret_cast<const float4 *>(plane);
@@ -779,10 +930,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                 }
             }
             if (kMode == kModeGroup && store) {
-                group_sync(grp);   // every stream's plane of frame f is complete
-                if (grp.shape == 3) group_store_frame_general(p, grp.planes, grp.q0, grp.T, p.pcm + off * p.C, kFrame >> sh);
-                else group_store_frame(grp, p.pcm + off * p.C, niter);
-                grp.pending = true;   // ... and must stay intact until the whole group is through this pass
+                mbar_arrive(grp.full);   // this warp's plane of frame f is complete (release) ...
+                grp.nstored++;
+                grp.pending = true;      // ... and stays intact until the store warps have arrived on `empty`
             }
             flag = next_flag;
             tr1 = next_tr1;
@@ -797,11 +947,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             }
         }
         __syncwarp();
-        if (dynamic && kMode == kModeGroup) {   // the group's first warp claims, the others read it after a group barrier
-            unsigned long long *slot0 = &wsmem[warp - slot].pad_;
-            if (slot == 0 && lane == 0) *slot0 = atomicAdd(p.work_counter, 1ULL) + (unsigned long long)item_stride;
-            group_sync(grp);
-            item = (long long)*slot0;
+        if (dynamic && kMode == kModeGroup) {
+            item = slot == 0 ? claimed : group_next_item(gws->claim, seq);
         } else if (dynamic) {
             unsigned long long next = 0;
             if (lane == 0) next = atomicAdd(p.work_counter, 1ULL) + (unsigned long long)item_stride;
@@ -810,7 +957,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             item += item_stride;
         }
     }
-    // (a pending group barrier needs no partner at exit: nobody overwrites a plane any more)
+    // (group mode: the store warps finish the last frame on their own; nobody overwrites a plane any more)
 }
 
 template <int kMode, int kWarps>
@@ -822,10 +969,10 @@ static cudaError_t prepare_variant(int smem)
 }
 
 template <int kMode, int kWarps>
-static void launch_variant(const SynthParams &p, unsigned grid, size_t smem, cudaStream_t stream)
+static void launch_variant(const SynthParams &p, unsigned grid, int warps, size_t smem, cudaStream_t stream)
 {
-    if (p.frame_offset) celt_synth_kernel<kMode, kWarps, true><<<grid, kWarps * 32, smem, stream>>>(p);
-    else celt_synth_kernel<kMode, kWarps, false><<<grid, kWarps * 32, smem, stream>>>(p);
+    if (p.frame_offset) celt_synth_kernel<kMode, kWarps, true><<<grid, warps * 32, smem, stream>>>(p);
+    else celt_synth_kernel<kMode, kWarps, false><<<grid, warps * 32, smem, stream>>>(p);
 }
 
 // prepare / launch of the variants each part owns (warps = 12 or 14 for the group parts)
@@ -839,49 +986,59 @@ void launch_part3(const SynthParams &p, int warps, unsigned grid, size_t smem, c
 #if NQ_PART == 1
 cudaError_t prepare_part1(int smem)
 {
-    cudaError_t e = prepare_variant<kModeGroup, kWarpsPerCta>(smem);
-    return e != cudaSuccess ? e : prepare_variant<kModeGroup, 12>(smem);
+    return prepare_variant<kModeGroup, 16>(smem);
 }
 void launch_part1(const SynthParams &p, int warps, unsigned grid, size_t smem, cudaStream_t stream)
 {
-    if (warps == 12) launch_variant<kModeGroup, 12>(p, grid, smem, stream);
-    else launch_variant<kModeGroup, kWarpsPerCta>(p, grid, smem, stream);
+    launch_variant<kModeGroup, 16>(p, grid, warps, smem, stream);
 }
 #elif NQ_PART == 2
 cudaError_t prepare_part2(int smem)
 {
-    cudaError_t e = prepare_variant<kModeGroupPaired, kWarpsPerCta>(smem);
-    return e != cudaSuccess ? e : prepare_variant<kModeGroupPaired, 12>(smem);
+    return prepare_variant<kModeGroupPaired, 16>(smem);
 }
 void launch_part2(const SynthParams &p, int warps, unsigned grid, size_t smem, cudaStream_t stream)
 {
-    if (warps == 12) launch_variant<kModeGroupPaired, 12>(p, grid, smem, stream);
-    else launch_variant<kModeGroupPaired, kWarpsPerCta>(p, grid, smem, stream);
+    launch_variant<kModeGroupPaired, 16>(p, grid, warps, smem, stream);
 }
 #elif NQ_PART == 3
 cudaError_t prepare_part3(int smem) { return prepare_variant<kModeDirect, kWarpsPerCta>(smem); }
 void launch_part3(const SynthParams &p, int, unsigned grid, size_t smem, cudaStream_t stream)
 {
-    launch_variant<kModeDirect, kWarpsPerCta>(p, grid, smem, stream);
+    launch_variant<kModeDirect, kWarpsPerCta>(p, grid, kWarpsPerCta, smem, stream);
 }
 #endif
 
 #if NQ_PART == 0
-// Warps per CTA of the group variant for this group width (see celt_synth_kernel): 12 unless only
-// 14 fits the group at all or doubles the groups of the CTA (7, 13 or 14 streams).
-static int group_cta_warps(int nstreams) { return nstreams == 7 || nstreams > 12 ? kWarpsPerCta : 12; }
+// Group mode, warp-specialised: a group is W synthesis warps (one per stream) served by SW store
+// warps; a CTA holds G groups and NS store warps, G the largest count that fits shared memory (14
+// synthesis warps), 16 warps per CTA and at most kMaxStoreUnits (group, part) units per store warp.
+int group_store_warps(int nstreams) { return nstreams >= 8 ? 2 : 1; }
 
 int groups_per_cta(int nstreams)
 {
-    return nstreams >= 1 && nstreams <= kMaxGroupStreams ? group_cta_warps(nstreams) / nstreams : 0;
+    if (nstreams < 1 || nstreams > kMaxGroupStreams) return 0;
+    const int SW = group_store_warps(nstreams);
+    int g = kWarpsPerCta / nstreams;
+    while (g > 1 && g * nstreams + (g * SW + kMaxStoreUnits - 1) / kMaxStoreUnits > 16) g--;
+    return g;
 }
 
-// Threads of a group that take part in the store pass: the largest T2 <= 32*nstreams with
-// 4*T2 a multiple of C (see GroupCtx); 0 if that leaves less than half of the group busy.
+// Store warps of a CTA: one per unit where 16 warps allow it (a multiple of SW, so that every unit
+// of a store warp is the same part of its group's frame).
+int group_store_warps_cta(int nstreams)
+{
+    const int G = groups_per_cta(nstreams), SW = group_store_warps(nstreams);
+    const int units = G * SW, room = 16 - G * nstreams;
+    return units <= room ? units : room / SW * SW;
+}
+
+// Threads of a group's store warps that take part in the store pass: the largest T2 <= 32*SW with
+// 4*T2 a multiple of C (see StoreCtx); 0 if that leaves less than half of them busy.
 int group_store_threads(int C, int nstreams)
 {
     int g = C % 4 == 0 ? 4 : (C % 2 == 0 ? 2 : 1);
-    const int m = C / g, T = 32 * nstreams;
+    const int m = C / g, T = 32 * group_store_warps(nstreams);
     const int T2 = (T / m) * m;
     return 2 * T2 >= T ? T2 : 0;
 }
@@ -910,22 +1067,23 @@ cudaError_t prepare_kernels()
 cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream_t stream, int *launched_ctas)
 {
     long long per_cta = kWarpsPerCta, nitems = p.nruns * p.npairs;
-    int warps = kWarpsPerCta;
+    int warps = kWarpsPerCta, smem_warps = kWarpsPerCta;
     bool paired = false;
     if (mode == kModeGroup) {
-        per_cta = groups_per_cta(p.nstreams);
+        per_cta = p.groups_per_cta;
         nitems = p.nruns;
-        warps = group_cta_warps(p.nstreams);
+        smem_warps = p.groups_per_cta * p.nstreams;   // synthesis warps own a shared-memory slice, store warps do not
+        warps = smem_warps + p.store_warps_cta;
         for (int s = 0; s < p.nstreams; s++) paired = paired || p.streams[s].flag_col1 != p.streams[s].flag_col;
     }
     long long ctas = (nitems + per_cta - 1) / per_cta;
     if (ctas > num_sms) ctas = num_sms;   // persistent: one CTA per SM, warps stride over the items
     if (ctas < 1) ctas = 1;
     if (launched_ctas) *launched_ctas = (int)ctas;
-    const size_t smem = sizeof(FastTables) + (size_t)warps * sizeof(WarpSmem);
+    const size_t smem = sizeof(FastTables) + (size_t)smem_warps * sizeof(WarpSmem);
     const unsigned grid = (unsigned)ctas;
-    if (mode == kModeStereo) launch_variant<kModeStereo, kWarpsPerCta>(p, grid, smem, stream);
-    else if (mode == kModeMono) launch_variant<kModeMono, kWarpsPerCta>(p, grid, smem, stream);
+    if (mode == kModeStereo) launch_variant<kModeStereo, kWarpsPerCta>(p, grid, warps, smem, stream);
+    else if (mode == kModeMono) launch_variant<kModeMono, kWarpsPerCta>(p, grid, warps, smem, stream);
     else if (mode == kModeGroup && paired) launch_part2(p, warps, grid, smem, stream);
     else if (mode == kModeGroup) launch_part1(p, warps, grid, smem, stream);
     else launch_part3(p, warps, grid, smem, stream);

@@ -77,8 +77,11 @@ struct SynthParams {
     int D;                      // decoded channels per frame (coefficient rows)
     int C;                      // output channels (pcm row width); == D without a channel mapping
     int npairs;                 // kModeDirect: channel pairs per frame
-    int nstreams;               // kModeGroup: warps per group (coupled streams + pairs of mono streams)
-    int store_threads;          // kModeGroup: threads of a group in the store pass (group_store_threads())
+    int nstreams;               // kModeGroup: synthesis warps per group (coupled streams + pairs of mono streams)
+    int groups_per_cta;         // kModeGroup: groups a CTA holds (groups_per_cta())
+    int store_warps;            // kModeGroup: store warps per group (group_store_warps())
+    int store_warps_cta;        // kModeGroup: store warps per CTA (group_store_warps_cta())
+    int store_threads;          // kModeGroup: threads of a group's store warps in the store pass (group_store_threads())
     int store_shape;            // kModeGroup: loop shape of the store pass (0: 2 x LDS.64, 1: 4 x LDS.32, 2: with silent channels)
     int halo_lm_shift;          // 3 - LM of the halo frame
     int halo_transient;         // flag(s) of the halo frame: bit s = stream s (bit 0 for everybody if !flag_per_stream)
@@ -140,6 +143,8 @@ cudaError_t launch_post(const PostParams &p, int njobs, cudaStream_t stream);
 size_t fast_kernel_smem_bytes();
 int synth_mode(int D, int C, int nstreams, bool identity_map, bool one_decoder);
 int groups_per_cta(int nstreams);
+int group_store_warps(int nstreams);
+int group_store_warps_cta(int nstreams);
 int group_store_threads(int C, int nstreams);
 cudaError_t launch_synth(const SynthParams &p, int mode, int num_sms, cudaStream_t stream, int *launched_ctas);
 cudaError_t launch_mdct_generic(const MdctCall *d_calls, int ncalls, const GenericTables *d_tables, cudaStream_t stream);

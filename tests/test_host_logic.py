@@ -134,13 +134,14 @@ def test_plan_plain_layouts():
     assert mono["frames_per_run"] == 128
     c8 = nq.debug_plan(8)
     assert (c8["mode"], c8["warps_per_group"], c8["groups_per_cta"]) == (nq.MODE_GROUP, 4, 3)
-    assert c8["store_threads"] == 128 and c8["store_shape"] == 0 and not c8["paired_mono"]
+    # warp-specialised groups: 4 synthesis warps + 1 store warp each, 3 groups = 15 warps per CTA
+    assert c8["store_threads"] == 32 and c8["store_shape"] == 0 and not c8["paired_mono"]
     assert c8["frames_per_run"] == 64 and c8["post_ctas"] == 4
     c3 = nq.debug_plan(3)
     assert (c3["warps_per_group"], c3["groups_per_cta"]) == (2, 6)
-    assert c3["store_threads"] == 63 and c3["store_shape"] == 1      # 4*T2 must be a multiple of C = 3
+    assert c3["store_threads"] == 30 and c3["store_shape"] == 1      # 4*T2 must be a multiple of C = 3
     c6 = nq.debug_plan(6)
-    assert c6["store_threads"] == 96 and c6["store_shape"] == 1      # rows of 6 floats: float4s straddle pairs
+    assert c6["store_threads"] == 30 and c6["store_shape"] == 1      # rows of 6 floats: float4s straddle pairs
     # tiny batches: runs never shorter than 8 frames
     small = nq.debug_plan(2, nframes=100)
     assert small["frames_per_run"] == 8 and small["runs"] == 13
@@ -148,7 +149,7 @@ def test_plan_plain_layouts():
 
 def test_plan_multistream_layouts():
     s71 = nq.debug_plan(8, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7])
-    # 3 coupled streams + the 2 mono streams sharing one warp = 4 warps, 3 groups per 12-warp CTA
+    # 3 coupled streams + the 2 mono streams sharing one warp = 4 synthesis warps, 3 groups (+ 3 store warps) per CTA
     assert (s71["mode"], s71["warps_per_group"], s71["groups_per_cta"], s71["paired_mono"]) == (nq.MODE_GROUP, 4, 3, 1)
     assert s71["decoded_channels"] == 8 and s71["store_shape"] == 1 and not s71["identity"]
     # post stage: (0) (6) (1) (2,3) (4,5) (7): the mapping separates L and R of stream 0
@@ -162,7 +163,7 @@ def test_plan_multistream_layouts():
     dual = nq.debug_plan(2, 2, 0, [0, 1])
     assert (dual["mode"], dual["warps_per_group"], dual["paired_mono"]) == (nq.MODE_GROUP, 1, 1)
     seven = nq.debug_plan(14, 7, 7, list(range(14)))
-    assert (seven["warps_per_group"], seven["groups_per_cta"]) == (7, 2)   # the 14-warp variant
+    assert (seven["warps_per_group"], seven["groups_per_cta"]) == (7, 2)   # 14 synthesis + 2 store warps
     odd = nq.debug_plan(37, 1, 1, [(7 * i) % 2 if i % 5 else 255 for i in range(37)])
     assert (odd["mode"], odd["store_threads"], odd["store_shape"]) == (nq.MODE_GROUP, 0, 3)   # general store loop
     with pytest.raises(nq.NqError) as e:
