@@ -232,9 +232,10 @@ int plan_layout(const Layout &L, int num_sms, long long nframes, SynthParams *pp
             sd.flag_col = (uint8_t)(L.per_stream_flags ? s0 : 0);
             sd.flag_col1 = (uint8_t)(L.per_stream_flags && sd.nch == 2 ? s0 + 1 : sd.flag_col);
         }
-        // store-pass loop shape (celt_synth_kernels.cu group_store_frame): every float4 of an output
-        // row = two coupled streams' (L, R) in order -> vector loads; any silent channel -> masked loop
-        bool vec = L.C % 4 == 0, muted = false;
+        // store-pass loop shape (celt_synth_kernels.cu group_store_frame): every output channel pair
+        // (2k, 2k+1) = one coupled stream's (L, R) in order, so that either half of any float4 of the
+        // output is one 8-byte element of a plane -> vector loads; any silent channel -> masked loop
+        bool vec = L.C % 2 == 0, muted = false;
         for (int c = 0; c < L.C; c++) muted = muted || L.mapping[c] == 255;
         for (int c = 0; c + 1 < L.C && vec; c += 2) {
             const int d = L.mapping[c];

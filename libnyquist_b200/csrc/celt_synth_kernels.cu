@@ -94,6 +94,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// For waits that are expected to last microseconds (a store warp waiting for the next frame): sleep
+// between tries, so that the waiting warp leaves the issue slots to the others.
+__device__ __forceinline__ void mbar_wait_long(unsigned long long *bar, uint32_t parity, unsigned ns)
+{
+    while (!mbar_test_wait(bar, parity)) __nanosleep(ns);
+}
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
 __device__ __forceinline__ void tma_load_row(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
 {
@@ -672,7 +678,7 @@ __device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem 
         for (int k = 0; k < nunits; k++) {
             if (f[k] >= f1[k]) continue;
             WarpSmem *gws = ugws[k];
-            if (nunits == 1) mbar_wait(&gws->full, nstored[k] & 1);
+            if (nunits == 1) mbar_wait_long(&gws->full, nstored[k] & 1, 256);
             else if (!mbar_test_wait(&gws->full, nstored[k] & 1)) continue;
             any = true;
             const long long fr = f[k];
@@ -694,7 +700,7 @@ __device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem 
                 start_run(k);
             }
         }
-        if (!any) __nanosleep(100);   // several units, none ready: leave the issue slots to the synthesis warps
+        if (!any) __nanosleep(256);   // several units, none ready: leave the issue slots to the synthesis warps
     }
 }
 

@@ -145,7 +145,7 @@ def test_real_frames_recorded_from_bundled_opus_files(synth, tag):
     assert_parity(out[1:], pcm[1:], tag)
 
 
-@pytest.mark.parametrize("C", [1, 2, 3, 8])
+@pytest.mark.parametrize("C", [1, 2, 3, 4, 6, 8])
 @pytest.mark.parametrize("p_tr", [0.0, 0.05, 1.0])
 def test_synth_batch_many_runs_vs_oracle(synth, C, p_tr):
     """Enough frames for thousands of warp runs: exercises the run-boundary re-synthesis."""

@@ -141,7 +141,7 @@ def test_plan_plain_layouts():
     assert (c3["warps_per_group"], c3["groups_per_cta"]) == (2, 6)
     assert c3["store_threads"] == 30 and c3["store_shape"] == 1      # 4*T2 must be a multiple of C = 3
     c6 = nq.debug_plan(6)
-    assert c6["store_threads"] == 30 and c6["store_shape"] == 1      # rows of 6 floats: float4s straddle pairs
+    assert c6["store_threads"] == 30 and c6["store_shape"] == 0      # rows of 6 floats: either half of a float4 is one pair
     # tiny batches: runs never shorter than 8 frames
     small = nq.debug_plan(2, nframes=100)
     assert small["frames_per_run"] == 8 and small["runs"] == 13
