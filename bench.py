@@ -214,8 +214,8 @@ def extras(torch, np, nq, synth, dev, peak, with_cpu_baseline):
     for name, frames, streams, coupled, mapping, p_tr in (
             ("mono", 2_000_000, 1, 0, [0], P_TRANSIENT),
             ("stereo_all_transient", 1_000_000, 1, 1, [0, 1], 1.0),
-            ("surround_5.1_multistream", 400_000, 4, 2, [0, 4, 1, 2, 3, 5], P_TRANSIENT),
-            ("surround_7.1_multistream", 300_000, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7], P_TRANSIENT)):
+            ("surround_5.1_multistream", 1_200_000, 4, 2, [0, 4, 1, 2, 3, 5], P_TRANSIENT),
+            ("surround_7.1_multistream", 1_000_000, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7], P_TRANSIENT)):
         D = streams + coupled
         c = torch.empty((frames, D, 960), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g)
         t = (torch.rand((frames, streams), generator=g, device=dev) < p_tr).to(torch.uint8)
