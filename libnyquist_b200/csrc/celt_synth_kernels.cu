@@ -38,11 +38,14 @@
 //     global stores stay 128-bit and coalesced;
 //   * a mono stream pairs two consecutive frames as the warp's two channels;
 //   * channel layouts other than plain stereo / mono (3, 8 channels, Opus
-//     multistream with a channel mapping): a GROUP of warps, one per stream,
-//     walks the run in lock-step; each warp leaves its frame as a [960][2]
-//     plane in its (idle) transpose buffer, and after one named barrier the
-//     group writes the interleaved [960][C] frame with contiguous float4
-//     stores -- the multistream channel mapping is a gather in this pass.
+//     multistream with a channel mapping) are warp-specialised: a GROUP of
+//     synthesis warps, one per stream, works on the same run; each leaves its
+//     frame as a [960][2] plane in its (idle) transpose buffer and arrives on
+//     the group's `full` mbarrier; a STORE warp waits for it, writes the
+//     interleaved [960][C] frame with contiguous float4 stores -- the
+//     multistream channel mapping is a gather in this pass -- and arrives on
+//     `empty`, which a synthesis warp only waits for when it is about to
+//     overwrite its plane, well into the next frame.
 // No tensor cores: this is an FFT, not a dense contraction.
 #include <cstdlib>
 #include "celt_synth_kernels.cuh"

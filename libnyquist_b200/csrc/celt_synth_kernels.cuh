@@ -35,11 +35,12 @@ struct GenericTables {
 
 // How the fast kernel is specialised (template parameter):
 //   kModeStereo  D = C = 2, one warp per run, float4 {L,R,L,R} stores straight from registers;
-//   kModeGroup   any channel layout with <= kMaxGroupStreams streams: a GROUP of warps (one per
-//                stream = one coupled pair or one mono channel) walks a run together; every warp
-//                leaves its frame as a [960][2] plane in shared memory and the group then writes
-//                the interleaved [960][C] output frame with contiguous float4 stores, gathering
-//                output channel c from decoded channel mapping[c] (opus_multistream_decoder.c:260-299);
+//   kModeGroup   any channel layout with <= kMaxGroupStreams streams, warp-specialised: a GROUP of
+//                synthesis warps (one per stream = one coupled pair or one mono channel) works on a
+//                run; every warp leaves its frame as a [960][2] plane in shared memory, and the
+//                group's store warp writes the interleaved [960][C] output frame with contiguous
+//                float4 stores, gathering output channel c from decoded channel mapping[c]
+//                (opus_multistream_decoder.c:260-299);
 //   kModeDirect  more streams than a CTA has warps: channel pairs, scattered stores (slow, rare);
 //   kModeMono    D = C = 1: one warp per run like stereo, its two "channels" being two consecutive
 //                frames of the stream whenever they have the same block type.
