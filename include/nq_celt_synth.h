@@ -215,7 +215,10 @@ NQ_API int nq_celt_sink_create(nq_celt_sink **out, int channels, int streams, in
 NQ_API void nq_celt_sink_destroy(nq_celt_sink *sink);
 NQ_API const char *nq_celt_sink_last_error(const nq_celt_sink *sink);
 /* One decoded CELT frame of stream `stream` (opus_multistream order), in decode
- * order: freq [CC][N] as it stands at celt_decoder_clean.c:636 (CC = 2 for a
+ * order (pushes of DIFFERENT streams may come from different threads at the same
+ * time -- the streams of a multistream packet are independent decoders,
+ * opus_multistream_decoder.c:237-251 -- every other sink call belongs to one
+ * thread): freq [CC][N] as it stands at celt_decoder_clean.c:636 (CC = 2 for a
  * coupled stream, 1 for a mono one), N = 120 << LM, shortBlocks = 0 or 1 << LM
  * (:273-284), post = the comb_filter arguments of the frame (:660-669). */
 NQ_API int nq_celt_sink_push(nq_celt_sink *sink, int stream, const float *freq, int CC, int N, int shortBlocks,

@@ -9,6 +9,10 @@
 //            off by integration/overlay: the range decoder / PVQ / denormalisation run unchanged on
 //            the CPU and every frame's coefficients + side info land in an nq_celt_sink (pinned
 //            host memory).  The PCM opusfile hands back is a placeholder; only its COUNT is used.
+//            The streams of a multistream packet are independent decoders
+//            (opus_multistream_decoder.c:237-251): with more than one stream, opusfile's decode
+//            callback (op_set_decode_callback) splits the packet like opus_multistream_decode_native
+//            does and decodes the streams on helper threads at the same time.
 //   phase 2  batched inverse MDCT + overlap-add + multistream channel routing + post-filter +
 //            de-emphasis on the B200, one call per block of 2048 frames on the sink's worker thread
 //            WHILE phase 1 decodes the next block (nq_celt_sink_attach / _finish), float PCM
@@ -24,14 +28,40 @@
 #include "Decoders.h"
 #include "opus/opusfile/include/opusfile.h"
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iostream>
+#include <memory>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "nq_celt_synth.h"
 #include "nq_phase1_session.h"
+
+// ---- phase 1 across the streams of a multistream packet ------------------------------------
+// Internal entry points of the reference's libopus (opus_private.h:109-111, :140-145; compiled
+// into this library with the rest of src/OpusDependencies.c): what opus_multistream_decode_native
+// itself uses to split a packet into its self-delimited sub-packets and decode one of them.
+extern "C" {
+int opus_decode_native(OpusDecoder *st, const unsigned char *data, opus_int32 len, float *pcm, int frame_size,
+                       int decode_fec, int self_delimited, opus_int32 *packet_offset, int soft_clip);
+int opus_packet_parse_impl(const unsigned char *data, opus_int32 len, int self_delimited, unsigned char *out_toc,
+                           const unsigned char *frames[48], opus_int16 size[48], int *payload_offset,
+                           opus_int32 *packet_offset);
+}
+
+// (before `using namespace nqr`: the ctl macro names ::OpusDecoder unqualified, and nqr has a class of that name)
+static OpusDecoder *nq_stream_decoder(OpusMSDecoder *msd, int stream)
+{
+    OpusDecoder *dec = nullptr;
+    if (opus_multistream_decoder_ctl(msd, OPUS_MULTISTREAM_GET_DECODER_STATE(stream, &dec)) != OPUS_OK) return nullptr;
+    return dec;
+}
 
 using namespace nqr;
 
@@ -64,6 +94,141 @@ struct SinkHolder {
     nq_celt_sink *s = nullptr;
     ~SinkHolder() { nq_celt_sink_destroy(s); }
 };
+
+// Helper threads that live for one file: the work items of a packet are tiny (tens of
+// microseconds), so the helpers spin on a generation counter instead of sleeping on a condition
+// variable, and the loader's thread takes its share of the items.
+class StreamPool
+{
+public:
+    explicit StreamPool(int helpers)
+    {
+        for (int i = 0; i < helpers; i++) threads.emplace_back([this] { helper(); });
+    }
+    ~StreamPool()
+    {
+        quit.store(true);
+        for (std::thread &t : threads) t.join();
+    }
+    // fn(item) for item in [0, n), in parallel; returns when all are done.
+    template <class F> void run(int n, F &&fn)
+    {
+        // (no helper is inside work() here: the previous run() waited for `active` to drop to zero)
+        job = [&](int i) { fn(i); };
+        total.store(n);
+        pending.store(n);
+        next.store(0);
+        generation.fetch_add(1);            // publishes job / total / pending / next to the helpers
+        work();
+        while (pending.load() > 0 || active.load() > 0) cpu_relax();
+    }
+
+private:
+    static void cpu_relax()
+    {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    void work()
+    {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= total.load()) return;
+            job(i);
+            pending.fetch_sub(1);
+        }
+    }
+    void helper()
+    {
+        unsigned long long seen = 0;
+        int idle = 0;
+        while (!quit.load()) {
+            const unsigned long long g = generation.load();
+            if (g == seen) {
+                if (++idle > 20000) std::this_thread::yield(); else cpu_relax();
+                continue;
+            }
+            seen = g;
+            idle = 0;
+            active.fetch_add(1);
+            work();
+            active.fetch_sub(1);
+        }
+        nq_phase1_bind(nullptr, -1);
+    }
+    std::vector<std::thread> threads;
+    std::function<void(int)> job;
+    std::atomic<int> total{0}, next{0}, pending{0}, active{0};
+    std::atomic<unsigned long long> generation{0};
+    std::atomic<bool> quit{false};
+};
+
+struct ParallelPhase1 {
+    nq_phase1_session *session = nullptr;
+    int streams = 0, coupled = 0;
+    std::unique_ptr<StreamPool> pool;
+    std::vector<std::vector<float>> pcm;   // per stream: the placeholder PCM opus_decode_native writes
+    struct Item {
+        ::OpusDecoder *dec;
+        const unsigned char *data;
+        opus_int32 len;
+        int ret;
+    };
+    std::vector<Item> items;
+};
+
+// op_decode_cb_func (opusfile.h): decode one packet of the link.  Mirrors
+// opus_multistream_decode_native (opus_multistream_decoder.c:183-300) minus the channel copy --
+// the PCM of phase 1 is a placeholder, only its length is used -- with the per-stream
+// opus_decode_native calls running at the same time.  Anything unusual (a lost packet, a packet
+// that does not parse) is left to the reference's own sequential path.
+int parallel_decode_cb(void *ctx, OpusMSDecoder *msd, void *pcm, const ogg_packet *op, int nsamples, int nchannels,
+                       int format, int /*li*/)
+{
+    ParallelPhase1 &pp = *static_cast<ParallelPhase1 *>(ctx);
+    if (format != OP_DEC_FORMAT_FLOAT || op->bytes < 2 * pp.streams - 1 || nsamples <= 0 || nsamples > 5760)
+        return OP_DEC_USE_DEFAULT;
+    const unsigned char *data = op->packet;
+    opus_int32 len = (opus_int32)op->bytes;
+    for (int s = 0; s < pp.streams; s++) {
+        unsigned char toc;
+        opus_int16 size[48];
+        opus_int32 packet_offset = 0;
+        if (len <= 0) return OP_DEC_USE_DEFAULT;
+        if (opus_packet_parse_impl(data, len, s != pp.streams - 1, &toc, nullptr, size, nullptr, &packet_offset) < 0)
+            return OP_DEC_USE_DEFAULT;
+        if (opus_packet_get_nb_samples(data, packet_offset, 48000) != nsamples) return OP_DEC_USE_DEFAULT;
+        ::OpusDecoder *dec = nq_stream_decoder(msd, s);
+        if (!dec) return OP_DEC_USE_DEFAULT;
+        pp.items[s] = {dec, data, len, 0};
+        data += packet_offset;
+        len -= packet_offset;
+    }
+    pp.pool->run(pp.streams, [&](int s) {
+        ParallelPhase1::Item &it = pp.items[s];
+        nq_phase1_bind(pp.session, s);
+        opus_int32 off = 0;
+        it.ret = opus_decode_native(it.dec, it.data, it.len, pp.pcm[s].data(), nsamples, 0, s != pp.streams - 1, &off, 0);
+    });
+    nq_phase1_bind(pp.session, -1);   // the loader's thread: back to first-seen order for the sequential path
+    for (int s = 0; s < pp.streams; s++)
+        if (pp.items[s].ret != nsamples) return pp.items[s].ret < 0 ? pp.items[s].ret : OPUS_INVALID_PACKET;
+    memset(pcm, 0, sizeof(float) * (size_t)nsamples * nchannels);
+    return 0;
+}
+
+int phase1_threads(int streams)
+{
+    int want = streams;
+    if (const char *e = getenv("NQ_PHASE1_THREADS")) want = atoi(e);   // 1: the sequential reference path
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && want > hw) want = hw;
+    if (want > streams) want = streams;
+    return want < 1 ? 1 : want;
+}
 
 }  // namespace
 
@@ -122,6 +287,17 @@ private:
         int64_t framesRead = 0;
         bool readError = false;
         nq_phase1_begin(sink.s);
+        ParallelPhase1 pp;
+        const int nthreads = phase1_threads(header->stream_count);
+        if (nthreads > 1) {
+            pp.session = nq_phase1_current();
+            pp.streams = header->stream_count;
+            pp.coupled = header->coupled_count;
+            pp.pcm.assign(pp.streams, std::vector<float>(size_t(5760) * 2));
+            pp.items.resize(pp.streams);
+            pp.pool.reset(new StreamPool(nthreads - 1));
+            op_set_decode_callback(fileHandle, parallel_decode_cb, &pp);
+        }
         for (;;) {
             const int n = op_read_float(fileHandle, placeholder.data(), (int)placeholder.size(), nullptr);
             if (n == 0) break;   // EOF
@@ -132,6 +308,8 @@ private:
             }
             framesRead += n;
         }
+        op_set_decode_callback(fileHandle, nullptr, nullptr);
+        pp.pool.reset();   // helpers joined before the session goes away
         const nq_phase1_stats st = nq_phase1_end();
         const double t1 = now_s();
 

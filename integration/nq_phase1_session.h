@@ -9,5 +9,14 @@ struct nq_phase1_stats {
     int error;            // first nq_celt_sink_push error, or 0
 };
 
+// One decode session per calling thread: the loader brackets its op_read_float loop with these.
 void nq_phase1_begin(nq_celt_sink *sink);
 nq_phase1_stats nq_phase1_end(void);
+
+// Phase 1 over the streams of a multistream packet in parallel (SURVEY.md section 8(f) row 2:
+// every multistream sub-decoder is independent, opus_multistream_decoder.c:237-251).
+// A session's helper threads decode streams 1.. while the session's own thread decodes stream 0;
+// each of them must say which stream the frames it is about to decode belong to.
+struct nq_phase1_session;
+nq_phase1_session *nq_phase1_current(void);                       // the calling thread's session (or null)
+void nq_phase1_bind(nq_phase1_session *session, int stream);      // this thread now decodes `stream` of `session`; -1: first-seen order

@@ -144,6 +144,8 @@ struct nq_celt_sink {
     unsigned char mapping[256] = {};
     std::deque<Block> blocks;        // blocks[k] holds frames [(first_block + k) * 2048, ...)
     long long first_block = 0;       // blocks already handed to the worker (streaming mode)
+    std::mutex push_mu;              // pushes of DIFFERENT streams may come from different threads (phase 1
+                                     // decodes the streams of a multistream packet in parallel)
     std::vector<long long> pushed;   // frames pushed per stream since the last flush / attach
     std::vector<char> reset_next;    // the stream's next frame follows a decoder reset (flag bit 3)
     // decoder state between phase-2 calls (have_state == false: reset decoder)
@@ -338,10 +340,21 @@ int nq_celt_sink_push(nq_celt_sink *s, int stream, const float *freq, int CC, in
         if (N == (120 << k)) LM = k;
     if (LM < 0 || post->N != N) return sink_fail(s, NQ_BAD_ARG, "frame size must be 120 << LM and equal post->N");
     if (shortBlocks != 0 && shortBlocks != (1 << LM)) return sink_fail(s, NQ_BAD_ARG, "shortBlocks must be 0 or 1 << LM");
-    const long long f = s->pushed[stream];
-    const size_t k = (size_t)(f / kBlockFrames - s->first_block), fi = (size_t)(f % kBlockFrames);
-    if (!ensure_block(s, k)) return sink_fail(s, NQ_ALLOC_FAIL, "pinned host memory");
-    Block &b = s->blocks[k];
+    // The block list is shared between the streams; a frame's rows inside a block are the
+    // stream's own.  So: find the block under the lock, copy outside it, publish under the lock.
+    // (The block cannot leave the list meanwhile: it is handed to the worker only when EVERY
+    // stream has published its last frame in it.)
+    long long f;
+    size_t fi;
+    Block b;
+    {
+        std::lock_guard<std::mutex> lk(s->push_mu);
+        f = s->pushed[stream];
+        const size_t k = (size_t)(f / kBlockFrames - s->first_block);
+        fi = (size_t)(f % kBlockFrames);
+        if (!ensure_block(s, k)) return sink_fail(s, NQ_ALLOC_FAIL, "pinned host memory");
+        b = s->blocks[k];
+    }
     const int row = stream < s->coupled ? 2 * stream : stream + s->coupled;
     for (int c = 0; c < nch; c++)   // rows keep the 960-float stride whatever the frame size
         memcpy(b.coef + (fi * s->D + row + c) * kFrame, freq + (size_t)c * N, sizeof(float) * N);
@@ -349,6 +362,7 @@ int nq_celt_sink_push(nq_celt_sink *s, int stream, const float *freq, int CC, in
     b.flags[fi * s->streams + stream] = (uint8_t)((shortBlocks > 1 ? 1 : 0) | ((3 - LM) << 1) | (s->reset_next[stream] ? 8 : 0));
     s->reset_next[stream] = 0;
     b.post[fi * s->streams + stream] = *post;
+    std::lock_guard<std::mutex> lk(s->push_mu);
     s->pushed[stream] = f + 1;
     // streaming: hand every complete block to the worker
     if (s->ctx && min_pushed(s) >= (s->first_block + 1) * kBlockFrames) {
@@ -358,7 +372,7 @@ int nq_celt_sink_push(nq_celt_sink *s, int stream, const float *freq, int CC, in
         s->blocks.pop_front();
         s->first_block++;
         {
-            std::lock_guard<std::mutex> lk(s->mu);
+            std::lock_guard<std::mutex> qlk(s->mu);
             s->queue.push_back(job);
         }
         s->cv.notify_all();

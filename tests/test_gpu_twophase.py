@@ -96,6 +96,31 @@ def test_nyquistio_load_two_phase_8_channel_multistream(twophase):
           f"vs reference Load {t_ref * 1e3:.0f} ms; max |err| {err:.2e}")
 
 
+def test_parallel_phase1_over_streams_equals_sequential(twophase, monkeypatch):
+    """the streams of a multistream packet are entropy-decoded on
+    helper threads at the same time (opusfile decode callback -> opus_decode_native per stream,
+    pushes of different streams racing into the sink).  The PCM must be bit-identical to the
+    sequential reference path (NQ_PHASE1_THREADS=1), load after load."""
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "surround8.opus")
+    monkeypatch.setenv("NQ_PHASE1_THREADS", "1")
+    load(twophase, path)
+    seq, ch, _, tm_seq, wall_seq = load(twophase, path)
+    assert seq is not None and ch == 8
+    monkeypatch.delenv("NQ_PHASE1_THREADS")
+    walls, p1 = [], []
+    for _ in range(12):
+        par, ch, _, tm, wall = load(twophase, path)
+        assert par is not None and par.shape == seq.shape and np.array_equal(par, seq)
+        walls.append(wall)
+        p1.append(tm[0])
+    monkeypatch.setenv("NQ_PHASE1_THREADS", "2")
+    two, *_ = load(twophase, path)
+    assert np.array_equal(two, seq)
+    print(f"\nsurround8.opus phase 1: sequential {tm_seq[0] * 1e3:.1f} ms (Load {wall_seq * 1e3:.1f} ms), "
+          f"5 streams in parallel {min(p1) * 1e3:.1f} ms (Load {min(walls) * 1e3:.1f} ms)")
+
+
 @pytest.mark.parametrize("gain_q8", [-1536, 768])
 def test_header_gain_is_applied_like_the_reference(twophase, tmp_path, gain_q8):
     """OpusHead.output_gain (opusfile OP_HEADER_GAIN -> OPUS_SET_GAIN -> opus_decoder_clean.c:578-588):
