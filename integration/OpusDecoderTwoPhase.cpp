@@ -69,21 +69,43 @@ static const int OPUS_SAMPLE_RATE = 48000;
 
 namespace {
 
-double g_last_timing[3] = {0, 0, 0};   // phase 1, phase 2, trim/gain (seconds) of the last Load
+thread_local double g_last_timing[3] = {0, 0, 0};   // phase 1, phase 2, trim/gain (seconds) of this thread's last Load
 
-nq_celt_ctx *device_context()
+// A context is not re-entrant (nq_celt_synth.h), but nqr::NyquistIO::Load may be called from
+// several threads at once, as the reference's can: every Load leases a context of its own from a
+// process-wide pool (created on demand, kept for the next Load).
+class ContextLease
 {
-    static std::mutex mu;
-    static nq_celt_ctx *ctx = nullptr;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!ctx) {
-        int rc = nq_celt_ctx_create(0, &ctx);
+public:
+    ContextLease()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu());
+            if (!idle().empty()) {
+                ctx_ = idle().back();
+                idle().pop_back();
+                return;
+            }
+        }
+        const int rc = nq_celt_ctx_create(0, &ctx_);
         if (rc != NQ_OK)
             throw std::runtime_error(std::string("two-phase Opus decoder: no usable B200 (") + nq_celt_strerror(rc) +
                                      "); this build has no CPU synthesis");
     }
-    return ctx;
-}
+    ~ContextLease()
+    {
+        std::lock_guard<std::mutex> lk(mu());
+        idle().push_back(ctx_);
+    }
+    ContextLease(const ContextLease &) = delete;
+    ContextLease &operator=(const ContextLease &) = delete;
+    nq_celt_ctx *get() const { return ctx_; }
+
+private:
+    static std::mutex &mu() { static std::mutex m; return m; }
+    static std::vector<nq_celt_ctx *> &idle() { static std::vector<nq_celt_ctx *> v; return v; }
+    nq_celt_ctx *ctx_ = nullptr;
+};
 
 double now_s()
 {
@@ -270,6 +292,7 @@ private:
     bool decodeTwoPhase(const OpusHead *header, int64_t totalSamples)
     {
         const int ch = d->channelCount;
+        ContextLease ctx;   // (declared before the sink: the sink's worker thread uses it until the sink is destroyed)
         SinkHolder sink;
         if (nq_celt_sink_create(&sink.s, ch, header->stream_count, header->coupled_count, header->mapping) != NQ_OK)
             throw std::runtime_error("two-phase Opus decoder: unsupported channel layout");
@@ -280,7 +303,7 @@ private:
         // to the final granule position (opusfile.c:2673-2721) ----
         const int64_t preSkip = header->pre_skip;
         float *out = d->samples.data();
-        if (nq_celt_sink_attach(sink.s, device_context(), out, preSkip, totalSamples) != NQ_OK)
+        if (nq_celt_sink_attach(sink.s, ctx.get(), out, preSkip, totalSamples) != NQ_OK)
             throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(sink.s));
         const double t0 = now_s();
         std::vector<float> placeholder(size_t(5760) * ch);   // 120 ms, the largest Opus packet

@@ -121,6 +121,37 @@ def test_parallel_phase1_over_streams_equals_sequential(twophase, monkeypatch):
           f"5 streams in parallel {min(p1) * 1e3:.1f} ms (Load {min(walls) * 1e3:.1f} ms)")
 
 
+def test_concurrent_loads_from_several_threads(twophase):
+    """nqr::NyquistIO::Load is callable from several threads at once in the reference (the CPU
+    decoder has no shared state); here every Load leases its own device context."""
+    import threading
+    from conftest import GOLDEN
+    paths = [os.path.join(GOLDEN, "surround8.opus")]
+    short = os.path.join(os.path.dirname(ref.LIB_PATH), "test_data", "short.opus")
+    if os.path.exists(short):
+        paths.append(short)
+    want = {p: load(twophase, p)[0] for p in paths}
+    assert all(w is not None for w in want.values())
+    results = {}
+
+    def work(i):
+        p = paths[i % len(paths)]
+        out = []
+        for _ in range(3):
+            out.append(load(twophase, p)[0])
+        results[i] = (p, out)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(results) == 6
+    for p, outs in results.values():
+        for got in outs:
+            assert got is not None and np.array_equal(got, want[p])
+
+
 @pytest.mark.parametrize("gain_q8", [-1536, 768])
 def test_header_gain_is_applied_like_the_reference(twophase, tmp_path, gain_q8):
     """OpusHead.output_gain (opusfile OP_HEADER_GAIN -> OPUS_SET_GAIN -> opus_decoder_clean.c:578-588):
