@@ -133,6 +133,21 @@ static_assert((kInRowFloats * 4) % 16 == 0, "TMA destination rows must be 16-byt
 
 constexpr int kPlaneOffFloats = 2 * kInRowFloats;   // offsetof(WarpSmem, x) / 4
 
+// Short-block frames park their finished samples in the channel's own (consumed) coefficient
+// row.  Sample n of channel c sits at ws.in[park_index(c, n)]: rows of 120 samples per sub-block,
+// the second half of the frame shifted by 4 floats and channel 1 by 2 -- the 32 lanes (channel,
+// sub-block, half) of a parking store then hit 32 different banks (plain rows: 120 b = 24 b mod 32
+// puts sub-blocks b and b + 4, and both channels, on the same banks: 4-way conflicts, 240 of the
+// short path's 900 shared-memory wavefronts per frame).  The 8 floats of padding per row hold it.
+// kModeMono keeps channel 1 (the next frame of the stream) 16-byte aligned instead: its frames
+// leave as float4 copies of the rows, which is worth more there than the last factor of two.
+template <int kMode>
+__device__ __forceinline__ int park_index(int c, int n)
+{
+    return c * (kInRowFloats + (kMode == kModeMono ? 0 : 2)) + n + (n >= kFrame / 2 ? 4 : 0);
+}
+
+
 // This file is compiled four times (-DNQ_PART=0..3, libnyquist_b200/build.py) so the kernel
 // instantiations build in parallel: part 0 = stereo + mono variants, the generic kernel and the
 // host-side dispatch; part 1 = group variants; part 2 = group variants with paired mono streams;
@@ -469,7 +484,7 @@ __device__ __forceinline__ void short_stage2(const FastTables &tb, WarpSmem &ws,
     const bool mine = !kPaired || ((vmask >> c) & 1);   // bit c = this channel is transient in this frame
     const float2 *a_own = ws.x + c * kXChanF2 + r * kXRowF2;
     const float2 *a_oth = ws.x + c * kXChanF2 + (r ^ 1) * kXRowF2;
-    float *stage = ws.in + c * kInRowFloats + 120 * b;
+    float *stage = ws.in + park_index<kMode>(c, 120 * b);
     // kModeMono: c = 1 is the NEXT frame of the same stream; its block 0 follows block 7 of c = 0 (lane - 2)
     float *tail = ws.tail + (kMode == kModeMono ? 0 : c * kHalfOvl);
     const bool tail_from_smem = b == 0 && (kMode != kModeMono || c == 0);
@@ -503,13 +518,13 @@ template <int kModeT>
 __device__ __forceinline__ void short_output(const SynthParams &p, WarpSmem &ws, int lane, long long off, int cb, int nch, bool store)
 {
     constexpr int kMode = kModeT == kModeGroupPaired ? kModeGroup : kModeT;
-    const float *L = ws.in, *R = ws.in + kInRowFloats;
     if (kMode == kModeGroup) {   // the stream's [960][2] plane for the group's store pass
         float4 *pl = reinterpret_cast<float4 *>(ws.x);
 #pragma unroll 5
         for (int j = 0; j < 15; j++) {
-            const int n = 2 * (lane + 32 * j);
-            const float2 l = *reinterpret_cast<const float2 *>(L + n), rr = *reinterpret_cast<const float2 *>(R + n);
+            const int n = 2 * (lane + 32 * j);   // (n even: the pair n, n + 1 never straddles the shifted half)
+            const float2 l = *reinterpret_cast<const float2 *>(ws.in + park_index<kMode>(0, n));
+            const float2 rr = *reinterpret_cast<const float2 *>(ws.in + park_index<kMode>(1, n));
             pl[n >> 1] = make_float4(l.x, rr.x, l.y, rr.y);
         }
     } else if (!store) {
@@ -518,20 +533,21 @@ __device__ __forceinline__ void short_output(const SynthParams &p, WarpSmem &ws,
 #pragma unroll 5
         for (int j = 0; j < 15; j++) {
             const int n = 2 * (lane + 32 * j);
-            const float2 l = *reinterpret_cast<const float2 *>(L + n), rr = *reinterpret_cast<const float2 *>(R + n);
+            const float2 l = *reinterpret_cast<const float2 *>(ws.in + park_index<kMode>(0, n));
+            const float2 rr = *reinterpret_cast<const float2 *>(ws.in + park_index<kMode>(1, n));
             __stcs(dst + (n >> 1), make_float4(l.x, rr.x, l.y, rr.y));
         }
     } else if (kMode == kModeMono) {
         for (int ch = 0; ch < nch; ch++) {
-            const float4 *s4 = reinterpret_cast<const float4 *>(ws.in + ch * kInRowFloats);
             float4 *dst = reinterpret_cast<float4 *>(p.pcm + off + ch * kFrame);
-            for (int j = lane; j < kFrame / 4; j += 32) __stcs(dst + j, s4[j]);
+            for (int j = lane; j < kFrame / 4; j += 32)
+                __stcs(dst + j, *reinterpret_cast<const float4 *>(ws.in + park_index<kMode>(ch, 4 * j)));
         }
     } else {   // kModeDirect
         float *dst = p.pcm + off * p.C + cb;
         for (int idx = lane; idx < 2 * kFrame; idx += 32) {
             const int n = idx >> 1, ch = idx & 1;
-            if (ch < nch) dst[n * p.C + ch] = ws.in[ch * kInRowFloats + n];
+            if (ch < nch) dst[n * p.C + ch] = ws.in[park_index<kMode>(ch, n)];
         }
     }
     __syncwarp();   // ws.in may be refilled
@@ -912,9 +928,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                 }
                 if (kPaired && split) {
                     __syncwarp();
-                    const float *src = ws.in + cs * kInRowFloats;
                     float *col = reinterpret_cast<float *>(ws.x) + cs;
-                    for (int n = lane; n < kFrame; n += 32) col[2 * n] = src[n];
+                    for (int n = lane; n < kFrame; n += 32) col[2 * n] = ws.in[park_index<kMode>(cs, n)];
                     __syncwarp();
                     if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch);
                 }

@@ -6,6 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import libnyquist_b200 as nq
 
+if os.environ.get("NQ_PROBE_LIB"):   # A/B runs: another build of the library
+    nq.LIB_PATH = os.environ["NQ_PROBE_LIB"]
+
 def run(synth, frames, C, p_tr, steps=5):
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(1)
