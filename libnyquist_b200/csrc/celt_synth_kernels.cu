@@ -645,6 +645,10 @@ __device__ __forceinline__ long long group_next_item(const volatile unsigned lon
 // layouts with many narrow groups): it polls their `full` barriers, writes the unit's part of the
 // interleaved frame and releases the planes.  Every unit walks the same runs and frames as the
 // synthesis warps of its group.
+#ifndef NQ_STORE_SLEEP_NS
+#define NQ_STORE_SLEEP_NS 256
+#endif
+constexpr unsigned kStoreSleepNs = NQ_STORE_SLEEP_NS;   // a store warp's nap between polls of its `full` barriers
 constexpr int kMaxStoreUnits = 3;   // 12 groups of one synthesis warp over 4 store warps (more per store warp measured slower: 7 x 2 + 2 warps 0.79, 6 x 2 + 4 warps 0.90)
 
 template <bool kAnySize>
@@ -698,7 +702,7 @@ __device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem 
         for (int k = 0; k < nunits; k++) {
             if (f[k] >= f1[k]) continue;
             WarpSmem *gws = ugws[k];
-            if (nunits == 1) mbar_wait_long(&gws->full, nstored[k] & 1, 256);
+            if (nunits == 1) mbar_wait_long(&gws->full, nstored[k] & 1, kStoreSleepNs);
             else if (!mbar_test_wait(&gws->full, nstored[k] & 1)) continue;
             any = true;
             const long long fr = f[k];
@@ -720,7 +724,7 @@ __device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem 
                 start_run(k);
             }
         }
-        if (!any) __nanosleep(256);   // several units, none ready: leave the issue slots to the synthesis warps
+        if (!any) __nanosleep(kStoreSleepNs);   // several units, none ready: leave the issue slots to the synthesis warps
     }
 }
 
