@@ -366,7 +366,10 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
     }
 }
 
-__global__ void __launch_bounds__(kPostThreads, 5) celt_post_kernel(const __grid_constant__ PostParams p)
+#ifndef NQ_POST_MIN_BLOCKS
+#define NQ_POST_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(kPostThreads, NQ_POST_MIN_BLOCKS) celt_post_kernel(const __grid_constant__ PostParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PostSmem &sm = *reinterpret_cast<PostSmem *>(smem_raw);

@@ -6,6 +6,9 @@ import numpy as np
 import torch
 import libnyquist_b200 as nq
 
+if os.environ.get("NQ_PROBE_LIB"):   # A/B runs: another build of the library
+    nq.LIB_PATH = os.environ["NQ_PROBE_LIB"]
+
 nseg, per = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, int(sys.argv[2]) if len(sys.argv) > 2 else 256
 frames = nseg * per
 rng = np.random.default_rng(3)
