@@ -22,9 +22,14 @@
 //            granule position (opusfile.c:2673-2721); opus_decode_frame applies the header gain
 //            (opus_decoder_clean.c:578-588).
 //
-// Scope: single-link, CELT-only streams (every bundled test file).  Chained links and SILK /
-// hybrid packets are refused with an exception -- there is no CPU synthesis in this build to fall
-// back to.
+// Scope: single-link files whose packets are all CELT-only (sb-reverie*.opus, short.opus, the
+// 8-channel file) or all SILK-only (test_data/ad_hoc/detodos.opus).  A SILK-only packet never
+// reaches celt_decode_with_ec (opus_decoder_clean.c:499-513): there is no CELT synthesis in it,
+// phase 1 -- the reference's own SILK decoder on the CPU -- IS its whole decode and the PCM
+// opusfile hands back is final.  Hybrid packets and files that switch between SILK and CELT mix
+// the two decoders sample by sample with redundancy frames and cross-fades
+// (opus_decoder_clean.c:553-600), which phase 2 does not reproduce: refused with an exception,
+// like chained links -- there is no CPU CELT synthesis in this build to fall back to.
 #include "Decoders.h"
 #include "opus/opusfile/include/opusfile.h"
 
@@ -191,6 +196,7 @@ private:
 struct ParallelPhase1 {
     nq_phase1_session *session = nullptr;
     int streams = 0, coupled = 0;
+    const unsigned char *mapping = nullptr;   // OpusHead.mapping
     std::unique_ptr<StreamPool> pool;
     std::vector<std::vector<float>> pcm;   // per stream: the placeholder PCM opus_decode_native writes
     struct Item {
@@ -203,9 +209,9 @@ struct ParallelPhase1 {
 };
 
 // op_decode_cb_func (opusfile.h): decode one packet of the link.  Mirrors
-// opus_multistream_decode_native (opus_multistream_decoder.c:183-300) minus the channel copy --
-// the PCM of phase 1 is a placeholder, only its length is used -- with the per-stream
-// opus_decode_native calls running at the same time.  Anything unusual (a lost packet, a packet
+// opus_multistream_decode_native (opus_multistream_decoder.c:183-300), channel routing included
+// (for CELT packets the PCM of phase 1 is a placeholder, for SILK-only ones it is the output),
+// with the per-stream opus_decode_native calls running at the same time.  Anything unusual (a lost packet, a packet
 // that does not parse) is left to the reference's own sequential path.
 int parallel_decode_cb(void *ctx, OpusMSDecoder *msd, void *pcm, const ogg_packet *op, int nsamples, int nchannels,
                        int format, int /*li*/)
@@ -238,7 +244,19 @@ int parallel_decode_cb(void *ctx, OpusMSDecoder *msd, void *pcm, const ogg_packe
     nq_phase1_bind(pp.session, -1);   // the loader's thread: back to first-seen order for the sequential path
     for (int s = 0; s < pp.streams; s++)
         if (pp.items[s].ret != nsamples) return pp.items[s].ret < 0 ? pp.items[s].ret : OPUS_INVALID_PACKET;
-    memset(pcm, 0, sizeof(float) * (size_t)nsamples * nchannels);
+    // channel routing, opus_multistream_decoder.c:260-299 (get_left/right/mono_channel, opus_multistream.c:57-91)
+    float *out = static_cast<float *>(pcm);
+    for (int c = 0; c < nchannels; c++) {
+        const int d = pp.mapping[c];
+        if (d == 255) {
+            for (int i = 0; i < nsamples; i++) out[(size_t)i * nchannels + c] = 0.f;
+            continue;
+        }
+        const bool is_coupled = d < 2 * pp.coupled;
+        const int s = is_coupled ? d / 2 : d - pp.coupled, stride = is_coupled ? 2 : 1;
+        const float *src = pp.pcm[s].data() + (is_coupled ? (d & 1) : 0);
+        for (int i = 0; i < nsamples; i++) out[(size_t)i * nchannels + c] = src[(size_t)i * stride];
+    }
     return 0;
 }
 
@@ -307,6 +325,7 @@ private:
             throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(sink.s));
         const double t0 = now_s();
         std::vector<float> placeholder(size_t(5760) * ch);   // 120 ms, the largest Opus packet
+        std::vector<float> cpuPcm;   // phase-1 PCM while no CELT frame has turned up: the output of a SILK-only file
         int64_t framesRead = 0;
         bool readError = false;
         nq_phase1_begin(sink.s);
@@ -316,6 +335,7 @@ private:
             pp.session = nq_phase1_current();
             pp.streams = header->stream_count;
             pp.coupled = header->coupled_count;
+            pp.mapping = header->mapping;
             pp.pcm.assign(pp.streams, std::vector<float>(size_t(5760) * 2));
             pp.items.resize(pp.streams);
             pp.pool.reset(new StreamPool(nthreads - 1));
@@ -330,6 +350,8 @@ private:
                 break;
             }
             framesRead += n;
+            if (nq_phase1_frames_so_far() == 0) cpuPcm.insert(cpuPcm.end(), placeholder.begin(), placeholder.begin() + size_t(n) * ch);
+            else if (!cpuPcm.empty()) std::vector<float>().swap(cpuPcm);
         }
         op_set_decode_callback(fileHandle, nullptr, nullptr);
         pp.pool.reset();   // helpers joined before the session goes away
@@ -341,8 +363,19 @@ private:
         const int rc = nq_celt_sink_finish(sink.s, &decoded);
         const double t2 = now_s();
         if (readError) return false;
+        if (st.saw_silk && st.frames == 0 && rc == NQ_OK && !st.error) {
+            // SILK-only file: no CELT frame anywhere, nothing for phase 2; opusfile has already
+            // applied pre-skip, end trim and the header gain to what it returned
+            if (framesRead != totalSamples || cpuPcm.size() != size_t(totalSamples) * ch)
+                throw std::runtime_error("two-phase Opus decoder: sample accounting does not match opusfile's");
+            memcpy(out, cpuPcm.data(), sizeof(float) * cpuPcm.size());
+            g_last_timing[0] = t1 - t0;
+            g_last_timing[1] = t2 - t1;
+            g_last_timing[2] = 0;
+            return totalSamples > 0;
+        }
         if (st.saw_silk)
-            throw std::runtime_error("two-phase Opus decoder: SILK / hybrid packets are not supported (CELT-only streams)");
+            throw std::runtime_error("two-phase Opus decoder: hybrid packets / files that mix SILK and CELT packets are not supported");
         if (st.error) throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(sink.s));
         if (st.frames && st.streams_seen != header->stream_count)
             throw std::runtime_error("two-phase Opus decoder: stream count mismatch");

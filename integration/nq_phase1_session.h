@@ -12,6 +12,7 @@ struct nq_phase1_stats {
 // One decode session per calling thread: the loader brackets its op_read_float loop with these.
 void nq_phase1_begin(nq_celt_sink *sink);
 nq_phase1_stats nq_phase1_end(void);
+long long nq_phase1_frames_so_far(void);   // CELT frames pushed by the calling thread's session so far
 
 // Phase 1 over the streams of a multistream packet in parallel (SURVEY.md section 8(f) row 2:
 // every multistream sub-decoder is independent, opus_multistream_decoder.c:237-251).

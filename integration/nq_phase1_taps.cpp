@@ -60,6 +60,8 @@ nq_phase1_stats nq_phase1_end(void)
 
 nq_phase1_session *nq_phase1_current(void) { return g_t.session; }
 
+long long nq_phase1_frames_so_far(void) { return g_t.session ? g_t.session->frames.load() : 0; }
+
 void nq_phase1_bind(nq_phase1_session *session, int stream)
 {
     g_t.session = session;
