@@ -65,7 +65,9 @@ if __name__ == "__main__":
             print(json.dumps(run_ms(s, int(fr), int(st), int(cp), float(p), int(sx[0]) if sx else 5)), flush=True)
         if cases or ms_cases:
             sys.exit(0)
+        for fr, st, cp in ((500_000, 5, 3), (600_000, 4, 2)):   # 7.1 / 5.1 multistream, own flags per stream
+            print(json.dumps(run_ms(s, fr, st, cp, 0.028)), flush=True)
         for frames, C, p in [(2_000_000, 2, 0.0), (2_000_000, 2, 0.028), (2_000_000, 2, 0.2), (2_000_000, 2, 1.0),
-                             (4_000_000, 1, 0.028), (500_000, 8, 0.028), (500_000, 8, 0.2), (1_300_000, 3, 0.028), (700_000, 6, 0.028),
+                             (4_000_000, 1, 0.028), (500_000, 8, 0.028), (500_000, 8, 0.2), (1_300_000, 3, 0.028), (700_000, 6, 0.028), (1_000_000, 4, 0.028),
                              (20_000, 2, 0.028), (2_000, 2, 0.028)]:
             print(json.dumps(run(s, frames, C, p)), flush=True)
