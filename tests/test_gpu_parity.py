@@ -159,6 +159,38 @@ def test_synth_batch_many_runs_vs_oracle(synth, C, p_tr):
     assert_parity(want_tail, tail, "tail")
 
 
+@pytest.mark.parametrize("C", [1, 2])
+def test_hybrid_start_band_17_and_narrow_end_bands(synth, C):
+    """the CELT layer of a hybrid frame starts at band 17
+    (opus_decoder_clean.c:443-444, CELT_SET_START_BAND) -- denormalise_bands leaves freq[] zero below
+    eBands[17] << LM = 40 << LM (celt_decoder_clean.c:620-636, static_modes_float.h eBands) -- and
+    narrower audio bandwidths end at band 13 / 17 / 19 (zero from eBands[end] << LM up).  For the
+    synthesis these are ordinary frames; long and short blocks, 10 and 20 ms (the hybrid sizes)."""
+    rng = np.random.default_rng(170 + C)
+    ebands = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 34, 40, 48, 60, 78, 100]
+    nframes = 240
+    lm = rng.choice([3, 2], nframes)
+    coef, tr = rand_batch(rng, nframes, C, 0.2)
+    for f in range(nframes):
+        M = 1 << lm[f]
+        start = rng.choice([0, 17])
+        end = rng.choice([13, 17, 19, 21]) if start == 0 else rng.choice([19, 21])
+        coef[f, :, :ebands[start] * M] = 0
+        coef[f, :, ebands[end] * M:] = 0
+    flags = (tr | ((3 - lm) << 1)).astype(np.uint8)
+    want, want_tail, offs = oracle_any_size(coef, flags, None)
+    import torch
+    if C == 2:
+        pcm, tail = synth.synth_batch_ms_torch(torch.from_numpy(coef).cuda(), torch.from_numpy(flags).cuda().reshape(-1, 1), 1, 1, None,
+                                               frame_offset=torch.from_numpy(offs).cuda())
+    else:
+        pcm, tail = synth.synth_batch_ms_torch(torch.from_numpy(coef).cuda(), torch.from_numpy(flags).cuda().reshape(-1, 1), 1, 0, None,
+                                               frame_offset=torch.from_numpy(offs).cuda())
+    torch.cuda.synchronize()
+    assert_parity(want, pcm.cpu().numpy(), f"hybrid-shaped frames C {C}")
+    assert_parity(want_tail, tail.cpu().numpy(), "tail")
+
+
 # ---- BASELINE config 4: Opus multistream layouts, interleave fused into the store pass ----
 def ms_oracle(coef, tr, streams, coupled, mapping, tail_in=None):
     """Per-stream compute_inv_mdcts (oracle) + the channel routing of
