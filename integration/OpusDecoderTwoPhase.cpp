@@ -22,14 +22,20 @@
 //            granule position (opusfile.c:2673-2721); opus_decode_frame applies the header gain
 //            (opus_decoder_clean.c:578-588).
 //
-// Scope: single-link files whose packets are all CELT-only (sb-reverie*.opus, short.opus, the
-// 8-channel file) or all SILK-only (test_data/ad_hoc/detodos.opus).  A SILK-only packet never
-// reaches celt_decode_with_ec (opus_decoder_clean.c:499-513): there is no CELT synthesis in it,
-// phase 1 -- the reference's own SILK decoder on the CPU -- IS its whole decode and the PCM
-// opusfile hands back is final.  Hybrid packets and files that switch between SILK and CELT mix
-// the two decoders sample by sample with redundancy frames and cross-fades
-// (opus_decoder_clean.c:553-600), which phase 2 does not reproduce: refused with an exception,
-// like chained links -- there is no CPU CELT synthesis in this build to fall back to.
+// Scope: single-link files that stay in ONE coding mode:
+//   CELT-only   (sb-reverie*.opus, short.opus, the 8-channel file): as above;
+//   SILK-only   (test_data/ad_hoc/detodos.opus): such a packet never reaches celt_decode_with_ec
+//               (opus_decoder_clean.c:499-513) -- there is no CELT synthesis in it, phase 1, the
+//               reference's own SILK decoder on the CPU, IS its whole decode and the PCM opusfile
+//               hands back is final;
+//   hybrid      the output is a plain sum (opus_decoder_clean.c:553-560): CELT layer above band 17
+//               + SILK layer / 32768.  With the CELT synthesis switched off, what opusfile hands
+//               back in phase 1 is the SILK layer alone, and the CELT layer comes out of phase 2
+//               like any other frame: AudioData.samples = phase-2 PCM + phase-1 PCM.
+// A file that SWITCHES modes decodes extra CELT frames into side buffers and cross-fades them in
+// (redundancy frames, the fade-out frame, concealment-based transitions: :478-487, :499-513,
+// :570-600), which phase 2 does not reproduce: refused with an exception, like chained links and
+// lost packets -- there is no CPU CELT synthesis in this build to fall back to.
 #include "Decoders.h"
 #include "opus/opusfile/include/opusfile.h"
 
@@ -350,7 +356,7 @@ private:
                 break;
             }
             framesRead += n;
-            if (nq_phase1_frames_so_far() == 0) cpuPcm.insert(cpuPcm.end(), placeholder.begin(), placeholder.begin() + size_t(n) * ch);
+            if (nq_phase1_frames_so_far() == 0 || nq_phase1_saw_silk_so_far()) cpuPcm.insert(cpuPcm.end(), placeholder.begin(), placeholder.begin() + size_t(n) * ch);
             else if (!cpuPcm.empty()) std::vector<float>().swap(cpuPcm);
         }
         op_set_decode_callback(fileHandle, nullptr, nullptr);
@@ -374,8 +380,8 @@ private:
             g_last_timing[2] = 0;
             return totalSamples > 0;
         }
-        if (st.saw_silk)
-            throw std::runtime_error("two-phase Opus decoder: hybrid packets / files that mix SILK and CELT packets are not supported");
+        if (st.saw_silk && (st.mode_switch || st.irregular_celt))
+            throw std::runtime_error("two-phase Opus decoder: files that switch between the SILK, hybrid and CELT coding modes (or conceal lost packets) are not supported");
         if (st.error) throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(sink.s));
         if (st.frames && st.streams_seen != header->stream_count)
             throw std::runtime_error("two-phase Opus decoder: stream count mismatch");
@@ -393,6 +399,13 @@ private:
         if (gainQ8 != 0) {
             const float gain = (float)std::exp(0.6931471805599453094 * (6.48814081e-4f * gainQ8));
             for (size_t i = 0; i < size_t(totalSamples) * ch; i++) out[i] = out[i] * gain;
+        }
+        if (st.saw_silk) {
+            // hybrid file: + the SILK layer, which phase 1 decoded, trimmed and scaled by the header gain
+            // already (opus_decoder_clean.c:553-560: pcm = celt + silk / 32768; the sum is linear)
+            if (cpuPcm.size() != size_t(totalSamples) * ch)
+                throw std::runtime_error("two-phase Opus decoder: sample accounting does not match opusfile's");
+            for (size_t i = 0; i < cpuPcm.size(); i++) out[i] = out[i] + cpuPcm[i];
         }
         g_last_timing[0] = t1 - t0;
         g_last_timing[1] = t2 - t1;

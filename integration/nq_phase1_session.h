@@ -5,7 +5,9 @@
 struct nq_phase1_stats {
     long long frames;     // CELT frames pushed (all streams)
     int streams_seen;     // distinct CELT decoder states, i.e. multistream streams
-    int saw_silk;         // a SILK / hybrid frame was decoded: not covered by phase 2
+    int saw_silk;         // silk_Decode ran: SILK-only or hybrid packets
+    int mode_switch;      // consecutive packets of different coding modes (redundancy frames, cross-fades, resets)
+    int irregular_celt;   // celt_decode_with_ec without packet data (concealment) or for less than 10 ms next to SILK
     int error;            // first nq_celt_sink_push error, or 0
 };
 
@@ -13,6 +15,7 @@ struct nq_phase1_stats {
 void nq_phase1_begin(nq_celt_sink *sink);
 nq_phase1_stats nq_phase1_end(void);
 long long nq_phase1_frames_so_far(void);   // CELT frames pushed by the calling thread's session so far
+int nq_phase1_saw_silk_so_far(void);
 
 // Phase 1 over the streams of a multistream packet in parallel (SURVEY.md section 8(f) row 2:
 // every multistream sub-decoder is independent, opus_multistream_decoder.c:237-251).

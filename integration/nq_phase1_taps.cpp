@@ -16,7 +16,7 @@ struct nq_phase1_session {
     nq_celt_sink *sink = nullptr;
     std::vector<const void *> decoders;   // unbound calls: CELT decoder states in first-seen order == stream order
     std::atomic<int> max_bound{-1};       // highest stream index a thread was bound to
-    std::atomic<bool> silk{false};
+    std::atomic<bool> silk{false}, mode_switch{false}, lost_celt{false}, short_celt{false};
     std::atomic<int> error{0};
     std::atomic<long long> frames{0};
 };
@@ -51,6 +51,9 @@ nq_phase1_stats nq_phase1_end(void)
         const int bound = s->max_bound.load() + 1;
         st.streams_seen = seen > bound ? seen : bound;
         st.saw_silk = s->silk.load() ? 1 : 0;
+        st.mode_switch = s->mode_switch.load() ? 1 : 0;
+        // (a CELT-only file may hold 2.5 / 5 ms frames of its own; next to SILK such calls are the mode-switch frames)
+        st.irregular_celt = (s->lost_celt.load() || (s->silk.load() && s->short_celt.load())) ? 1 : 0;
         st.error = s->error.load();
         delete s;
     }
@@ -61,6 +64,8 @@ nq_phase1_stats nq_phase1_end(void)
 nq_phase1_session *nq_phase1_current(void) { return g_t.session; }
 
 long long nq_phase1_frames_so_far(void) { return g_t.session ? g_t.session->frames.load() : 0; }
+
+int nq_phase1_saw_silk_so_far(void) { return g_t.session && g_t.session->silk.load() ? 1 : 0; }
 
 void nq_phase1_bind(nq_phase1_session *session, int stream)
 {
@@ -73,9 +78,21 @@ void nq_phase1_bind(nq_phase1_session *session, int stream)
     }
 }
 
-extern "C" void nq_phase1_note_silk(void)
+extern "C" void nq_phase1_note_silk(int mode, int prev_mode)
 {
-    if (g_t.session) g_t.session->silk.store(true);
+    nq_phase1_session *s = g_t.session;
+    if (!s) return;
+    s->silk.store(true);
+    if (prev_mode > 0 && prev_mode != mode) s->mode_switch.store(true);
+}
+
+extern "C" void nq_phase1_note_celt_call(int has_data, int frame_size, int mode, int prev_mode)
+{
+    nq_phase1_session *s = g_t.session;
+    if (!s) return;
+    if (!has_data) s->lost_celt.store(true);
+    if (frame_size < 480) s->short_celt.store(true);
+    if (prev_mode > 0 && prev_mode != mode) s->mode_switch.store(true);
 }
 
 extern "C" void nq_phase1_frame_tap(const void *dec, const float *freq, int CC, int N, int LM, int shortBlocks, int c,

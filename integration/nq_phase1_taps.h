@@ -12,7 +12,13 @@ extern "C" {
  * active sink when its last channel-0 call arrives. */
 void nq_phase1_frame_tap(const void *celt_decoder, const float *freq, int CC, int N, int LM, int shortBlocks, int c,
                          int T0, int T1, float g0, float g1, int tapset0, int tapset1);
-void nq_phase1_note_silk(void);
+/* silk_Decode is about to run for a packet of coding mode `mode` (MODE_SILK_ONLY 1000 / MODE_HYBRID
+ * 1001), the previous packet's having been `prev_mode` (0: none yet). */
+void nq_phase1_note_silk(int mode, int prev_mode);
+/* opus_decode_frame is about to call celt_decode_with_ec: with or without packet data (NULL: loss
+ * concealment), for `frame_size` samples (the 5 ms redundancy frames and the 2.5 ms fade-out frame
+ * of a mode switch are such calls). */
+void nq_phase1_note_celt_call(int has_data, int frame_size, int mode, int prev_mode);
 
 #ifdef __cplusplus
 }

@@ -191,6 +191,45 @@ def encode_surround(pcm: np.ndarray, bitrate: int = 512000) -> bytes:
     return out[:got].tobytes()
 
 
+MODE_SILK_ONLY, MODE_HYBRID, MODE_CELT_ONLY = 1000, 1001, 1002   # opus_private.h:90-92
+
+
+def encode_mode_switch(pcm: np.ndarray, mode_a: int, mode_b: int, switch_frame: int, bitrate: int = 40000) -> bytes:
+    """Like encode_forced_mode, switching from mode_a to mode_b at frame `switch_frame`."""
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    n, ch = pcm.shape
+    assert n % FRAME == 0 and ch in (1, 2)
+    cap = 1 << 22
+    out = np.zeros(cap, np.uint8)
+    L = lib()
+    L.nqref_encode_mode_switch.restype = C.c_long
+    L.nqref_encode_mode_switch.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long]
+    got = L.nqref_encode_mode_switch(pcm.ctypes.data_as(C.c_void_p), n, ch, int(bitrate), int(mode_a), int(mode_b),
+                                     int(switch_frame), out.ctypes.data_as(C.c_void_p), cap)
+    if got < 0:
+        raise RuntimeError(f"reference encoder failed: {got}")
+    return out[:got].tobytes()
+
+
+def encode_forced_mode(pcm: np.ndarray, mode: int, bitrate: int = 32000) -> bytes:
+    """The reference's own encoder (VOIP application) forced into one coding mode with the private
+    OPUS_SET_FORCE_MODE ctl: test files for the SILK / hybrid branches of opus_decode_frame
+    (opus_decoder_clean.c:340-600).  pcm [nsamples][1 or 2] float32, nsamples a multiple of 960."""
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    n, ch = pcm.shape
+    assert n % FRAME == 0 and ch in (1, 2)
+    cap = 1 << 22
+    out = np.zeros(cap, np.uint8)
+    L = lib()
+    L.nqref_encode_forced_mode.restype = C.c_long
+    L.nqref_encode_forced_mode.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long]
+    got = L.nqref_encode_forced_mode(pcm.ctypes.data_as(C.c_void_p), n, ch, int(bitrate), int(mode),
+                                     out.ctypes.data_as(C.c_void_p), cap)
+    if got < 0:
+        raise RuntimeError(f"reference encoder failed: {got}")
+    return out[:got].tobytes()
+
+
 def with_output_gain(data: bytes, gain_q8: int) -> bytes:
     """The same Ogg Opus file with OpusHead.output_gain (Q7.8 dB) rewritten and the page CRC fixed."""
     a = np.frombuffer(data, np.uint8).copy()

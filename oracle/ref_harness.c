@@ -351,8 +351,14 @@ static int put_page(ogg_stream_state *os, int flush, unsigned char *out, long ca
     return 0;
 }
 
-NQREF_API long nqref_encode_surround(const float *pcm, long nsamples, int channels, int bitrate,
-                                     unsigned char *out, long cap)
+/* force_mode: 0 = the encoder decides (RESTRICTED_LOWDELAY: CELT only), else MODE_SILK_ONLY (1000) /
+ * MODE_HYBRID (1001) / MODE_CELT_ONLY (1002) through the private OPUS_SET_FORCE_MODE ctl
+ * (opus_private.h:90-96), with the VOIP application -- test files for the SILK / hybrid paths of
+ * opus_decode_frame (opus_decoder_clean.c:340-600). */
+static int g_switch_frame = -1, g_switch_mode = 0;   /* nqref_encode_mode_switch: from this frame on, that mode */
+
+static long encode_ogg(const float *pcm, long nsamples, int channels, int bitrate, int force_mode,
+                       unsigned char *out, long cap)
 {
     int err = 0, streams = 0, coupled = 0, lookahead = 0, i;
     unsigned char mapping[255], head[32 + 255], pkt[8 * 1500];
@@ -362,9 +368,13 @@ NQREF_API long nqref_encode_surround(const float *pcm, long nsamples, int channe
     ogg_stream_state os;
     ogg_packet op;
     OpusMSEncoder *enc = opus_multistream_surround_encoder_create(48000, channels, channels > 2 ? 1 : 0, &streams, &coupled,
-                                                                  mapping, OPUS_APPLICATION_RESTRICTED_LOWDELAY, &err);
+                                                                  mapping, force_mode ? OPUS_APPLICATION_VOIP : OPUS_APPLICATION_RESTRICTED_LOWDELAY, &err);
     if (!enc || err != OPUS_OK) return -1;
     opus_multistream_encoder_ctl(enc, OPUS_SET_BITRATE(bitrate));
+    if (force_mode) {
+        opus_multistream_encoder_ctl(enc, OPUS_SET_FORCE_MODE(force_mode));
+        opus_multistream_encoder_ctl(enc, OPUS_SET_BANDWIDTH(force_mode == MODE_SILK_ONLY ? OPUS_BANDWIDTH_WIDEBAND : OPUS_BANDWIDTH_FULLBAND));
+    }
     opus_multistream_encoder_ctl(enc, OPUS_GET_LOOKAHEAD(&lookahead));
     if (ogg_stream_init(&os, 0x0B200) != 0) return -2;
     /* OpusHead, RFC 7845 section 5.1 */
@@ -394,7 +404,9 @@ NQREF_API long nqref_encode_surround(const float *pcm, long nsamples, int channe
     ogg_stream_packetin(&os, &op);
     if (put_page(&os, 1, out, cap, &pos)) return -3;
     for (f = 0; f < nframes; f++) {
-        int n = opus_multistream_encode_float(enc, pcm + f * FRAME * channels, FRAME, pkt, (opus_int32)sizeof pkt);
+        int n;
+        if (f == g_switch_frame) opus_multistream_encoder_ctl(enc, OPUS_SET_FORCE_MODE(g_switch_mode));
+        n = opus_multistream_encode_float(enc, pcm + f * FRAME * channels, FRAME, pkt, (opus_int32)sizeof pkt);
         if (n < 0) return -4;
         memset(&op, 0, sizeof op);
         op.packet = pkt; op.bytes = n; op.packetno = 2 + f;
@@ -409,6 +421,31 @@ NQREF_API long nqref_encode_surround(const float *pcm, long nsamples, int channe
     ogg_stream_clear(&os);
     opus_multistream_encoder_destroy(enc);
     return pos;
+}
+
+NQREF_API long nqref_encode_surround(const float *pcm, long nsamples, int channels, int bitrate,
+                                     unsigned char *out, long cap)
+{
+    return encode_ogg(pcm, nsamples, channels, bitrate, 0, out, cap);
+}
+
+NQREF_API long nqref_encode_forced_mode(const float *pcm, long nsamples, int channels, int bitrate, int force_mode,
+                                        unsigned char *out, long cap)
+{
+    return encode_ogg(pcm, nsamples, channels, bitrate, force_mode, out, cap);
+}
+
+/* A file that switches coding mode at `switch_frame` (the encoder inserts the redundancy frames and
+ * the decoder cross-fades, opus_decoder_clean.c:570-600): what the two-phase loader must refuse. */
+NQREF_API long nqref_encode_mode_switch(const float *pcm, long nsamples, int channels, int bitrate, int mode_a,
+                                        int mode_b, int switch_frame, unsigned char *out, long cap)
+{
+    long n;
+    g_switch_frame = switch_frame;
+    g_switch_mode = mode_b;
+    n = encode_ogg(pcm, nsamples, channels, bitrate, mode_a, out, cap);
+    g_switch_frame = -1;
+    return n;
 }
 
 /* Rewrites the output-gain field (Q7.8 dB, RFC 7845 section 5.1) of an in-memory Ogg Opus file's

@@ -19,6 +19,11 @@ Outputs (all small):
   surround8.opus     BASELINE config 4 stand-in for the missing Rachel8ch.opus: a 7.1 Ogg Opus file made
                      with the reference's own surround encoder from seeded synthetic audio
                      (+ surround8.json: what the reference decoder makes of it)
+  hybrid.opus, silk_stereo.opus
+                     SURVEY.md 8(f) row 4: a hybrid file (every packet SILK below 8 kHz + a CELT
+                     layer from band 17 up) and a stereo SILK-only one, made with the reference's
+                     own encoder forced into the mode (OPUS_SET_FORCE_MODE) from seeded synthetic
+                     speech-like audio (+ modes.json: what the reference decoder makes of them)
   post_cases.npz     SURVEY.md 8(f) row 1: single comb_filter / deemphasis calls of
                      the compiled reference on seeded inputs, and the LAST 26 frames
                      of short.opus (active post-filter, tapset changes, a transient
@@ -177,6 +182,30 @@ def main():
                "transient_records": int(sum(r["B"] == 8 for r in recs8)),
                "reference_pcm_sha256": hashlib.sha256(out8.tobytes()).hexdigest()},
               open(f"{HERE}/surround8.json", "w"), indent=1)
+    # ---- hybrid / SILK-only files (the coding modes of opus_decode_frame besides CELT-only) ----
+    n = 960 * 150
+    t = np.arange(n) / fs
+    rs = np.random.default_rng(0)
+    f0 = 140 + 30 * np.sin(2 * np.pi * 0.7 * t)
+    ph = np.cumsum(2 * np.pi * f0 / fs)
+    voiced = sum(np.sin(k * ph) / k for k in range(1, 30))
+    env = (0.5 + 0.5 * np.sin(2 * np.pi * 2.1 * t)) ** 2
+    sig = 0.25 * env * voiced / np.abs(voiced).max() + 0.03 * rs.standard_normal(n) * (1 - env)
+    sig += 0.02 * env * rs.standard_normal(n)       # content above 8 kHz for the CELT layer
+    speech = np.stack([sig, np.roll(sig, 37) * 0.8], 1).astype(np.float32)
+    info = {}
+    for name, mode, rate in (("hybrid", ref.MODE_HYBRID, 40000), ("silk_stereo", ref.MODE_SILK_ONLY, 24000)):
+        data = ref.encode_forced_mode(speech, mode, rate)
+        open(f"{HERE}/{name}.opus", "wb").write(data)
+        out, recs = ref.decode_bytes(data, record=True)
+        if mode == ref.MODE_HYBRID:   # one 20 ms CELT frame per packet, nothing below band 17 (bin 320)
+            assert len(recs) == 150 and all(r["coef"].shape[1] == 960 and not r["coef"][:, :320].any() for r in recs)
+        else:
+            assert len(recs) == 0
+        info[name] = {"samples_per_channel": int(out.shape[0]), "channels": int(out.shape[1]), "celt_frames": len(recs),
+                      "transient_frames": int(sum(r["B"] > 1 for r in recs)),
+                      "reference_pcm_sha256": hashlib.sha256(out.tobytes()).hexdigest()}
+    json.dump(info, open(f"{HERE}/modes.json", "w"), indent=1)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

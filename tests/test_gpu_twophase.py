@@ -186,6 +186,55 @@ def test_silk_only_file_decodes_through_phase_1(twophase):
     assert np.array_equal(got, want)
 
 
+def test_hybrid_file_celt_layer_on_the_gpu_plus_silk_layer_of_phase_1(twophase):
+    """SURVEY.md section 8(f) row 4, end to end: tests/golden/hybrid.opus (the reference's own encoder
+    forced into MODE_HYBRID: 150 packets, each a SILK layer + a 20 ms CELT frame starting at band 17,
+    47 of them transient).  opus_decode_frame sums the two layers (opus_decoder_clean.c:553-560); here
+    the CELT layer is synthesised in phase 2 and the SILK layer is what phase 1 hands back."""
+    import hashlib
+    import json
+    from conftest import GOLDEN
+    info = json.load(open(os.path.join(GOLDEN, "modes.json")))
+    for name, exact in (("hybrid", False), ("silk_stereo", True)):
+        path = os.path.join(GOLDEN, name + ".opus")
+        got, ch, sr, tm, wall = load(twophase, path)
+        assert got is not None and (ch, sr) == (2, 48000)
+        assert got.shape == (info[name]["samples_per_channel"], 2)
+        if ref.available():
+            want, recs = ref.decode_file(path, record=True)
+            assert hashlib.sha256(want.tobytes()).hexdigest() == info[name]["reference_pcm_sha256"]
+            assert len(recs) == info[name]["celt_frames"]
+            err = float(np.abs(got.astype(np.float64) - want).max())
+            assert err <= 1e-5 and snr_db(want, got) >= 100.0, (name, err)
+            if exact:
+                assert np.array_equal(got, want)
+            else:     # the CELT layer is really there: without it the error is orders of magnitude larger
+                assert float(np.abs(want).max()) > 0.1
+            print(f"\n{name}.opus: Load {wall * 1e3:.1f} ms, max |err| {err:.2e}")
+        elif exact:
+            assert hashlib.sha256(got.tobytes()).hexdigest() == info[name]["reference_pcm_sha256"]
+
+
+@pytest.mark.parametrize("a,b", [("hybrid", "celt"), ("celt", "hybrid")])
+def test_mode_switching_file_is_refused_not_misdecoded(twophase, tmp_path, a, b):
+    """A switch between coding modes makes opus_decode_frame decode 5 ms redundancy frames into side
+    buffers and cross-fade them in (opus_decoder_clean.c:478-487, :570-600) -- not a plain sum of
+    layers.  Load must fail loudly; the reference itself decodes the file."""
+    if not ref.available():
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    modes = {"hybrid": ref.MODE_HYBRID, "celt": ref.MODE_CELT_ONLY}
+    n = 960 * 60
+    t = np.arange(n) / 48000
+    sig = (0.2 * np.sin(2 * np.pi * 180 * t) + 0.05 * np.random.default_rng(1).standard_normal(n)).astype(np.float32)
+    data = ref.encode_mode_switch(np.stack([sig, sig * 0.7], 1), modes[a], modes[b], 30)
+    path = tmp_path / "switch.opus"
+    path.write_bytes(data)
+    want, recs = ref.decode_bytes(data, record=True)
+    assert want.shape[1] == 2 and any(r["coef"].shape[1] == 240 for r in recs)   # the redundancy frames are there
+    got, *_ = load(twophase, str(path))
+    assert got is None
+
+
 def test_two_phase_load_errors_like_the_reference(twophase, tmp_path):
     bad = tmp_path / "noise.opus"
     bad.write_bytes(np.random.default_rng(0).integers(0, 256, 5000, dtype=np.uint8).tobytes())
