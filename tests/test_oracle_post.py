@@ -110,3 +110,23 @@ def test_surround8_reference_decode_is_pinned_and_oracle_reproduces_it_bit_exact
     assert len({tuple(flags[f]) for f in range(len(flags))}) > 4, "streams should switch blocks independently"
     full = oracle_decode_multistream(coef, flags, frames, streams, coupled, mapping)
     assert np.array_equal(full[pre_skip:pre_skip + len(pcm)].view(np.uint32), pcm.view(np.uint32))
+
+
+# ---- the other coding modes of opus_decode_frame ----
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnq_ref.so not built (needs /root/reference)")
+def test_hybrid_and_silk_files_reference_decode_is_pinned():
+    """tests/golden/hybrid.opus / silk_stereo.opus were made with the reference's own encoder forced into
+    a coding mode (tests/golden/make_golden.py).  The reference decoder's PCM is pinned by hash; the
+    hybrid file's CELT layer is one 20 ms frame per packet with nothing below band 17 (bin 320), the
+    SILK-only file never reaches the CELT synthesis."""
+    import hashlib
+    import json
+    from conftest import GOLDEN
+    info = json.load(open(os.path.join(GOLDEN, "modes.json")))
+    for name, meta in info.items():
+        pcm, recs = ref.decode_file(os.path.join(GOLDEN, name + ".opus"), record=True)
+        assert pcm.shape == (meta["samples_per_channel"], meta["channels"]) and len(recs) == meta["celt_frames"]
+        assert hashlib.sha256(pcm.tobytes()).hexdigest() == meta["reference_pcm_sha256"]
+        assert sum(r["B"] > 1 for r in recs) == meta["transient_frames"]
+        for r in recs:
+            assert r["coef"].shape == (2, 960) and not r["coef"][:, :320].any() and r["coef"][:, 320:].any()
