@@ -5,6 +5,7 @@
 //   the fork's GPU seam processMDCTCuda*             cuda/mdct_cuda.hpp:79-103
 // and adds the batched phase-2 entry the restructured decoder calls once per
 // batch of frames.  No CPU fallback anywhere: every entry needs a CUDA device.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -870,32 +871,79 @@ static int post_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *f
     }
     if (!pcm || !frames) return fail(ctx, NQ_BAD_ARG, "null pcm/frames");
     if (reinterpret_cast<uintptr_t>(pcm) & 15) return fail(ctx, NQ_BAD_ARG, "pcm must be a 16-byte aligned device pointer");
-    for (int64_t i = 0; i < nframes * L.streams; i++) {
-        const nq_celt_post_frame &f = frames[i];
-        const int N0 = frames[(i / L.streams) * L.streams].N;
-        const bool okN = f.N == 120 || f.N == 240 || f.N == 480 || f.N == 960;
-        bool ok = okN && f.N == N0;
-        for (int k = 0; k < 3 && ok; k++) {
-            // a zero-gain filter is never evaluated, whatever its period (celt_decoder_clean.c passes pitch 0 then)
-            if (f.gain[k] != 0.f && (f.pitch[k] < 15 || f.pitch[k] > 1022)) ok = false;   // COMBFILTER_MINPERIOD .. 1022
-            if (f.tapset[k] < 0 || f.tapset[k] > 2) ok = false;
+    // One pass over the side information: validate it and note the first sample of every segment
+    // (this loop runs while the synthesis kernel of the same batch is still busy, so it should not
+    // take longer than that: no per-frame tables, nothing allocated per frame).
+    std::vector<long long> seg_first;
+    if (seg_start) {
+        if (nseg < 1 || seg_start[0] != 0 || seg_start[nseg] != nframes) return fail(ctx, NQ_BAD_ARG, "seg_start must run from 0 to nframes");
+        for (int k = 0; k < nseg; k++)
+            if (seg_start[k + 1] < seg_start[k]) return fail(ctx, NQ_BAD_ARG, "seg_start must be non-decreasing");
+        seg_first.assign(nseg, 0);
+    }
+    {
+        // frames [f0, f1): returns the first bad frame (or -1) and the samples they hold; segments
+        // that start inside the range get their first sample RELATIVE to the range's first sample
+        const int S = L.streams;
+        auto scan = [&](int64_t f0, int64_t f1, long long *samples) -> int64_t {
+            long long pos = 0;
+            int k = 0;
+            if (seg_start) k = (int)(std::lower_bound(seg_start, seg_start + nseg, f0) - seg_start);
+            for (int64_t fi = f0; fi < f1; fi++) {
+                while (seg_start && k < nseg && seg_start[k] == fi) seg_first[k++] = pos;
+                const nq_celt_post_frame *row = frames + fi * S;
+                const int N0 = row[0].N;
+                bool ok = N0 == 120 || N0 == 240 || N0 == 480 || N0 == 960;
+                for (int sidx = 0; sidx < S && ok; sidx++) {
+                    const nq_celt_post_frame &f = row[sidx];
+                    ok = f.N == N0;
+                    for (int j = 0; j < 3 && ok; j++) {
+                        // a zero-gain filter is never evaluated, whatever its period (celt_decoder_clean.c passes pitch 0 then)
+                        if (f.gain[j] != 0.f && (f.pitch[j] < 15 || f.pitch[j] > 1022)) ok = false;   // COMBFILTER_MINPERIOD .. 1022
+                        if (f.tapset[j] < 0 || f.tapset[j] > 2) ok = false;
+                    }
+                }
+                if (!ok) return fi;
+                pos += N0;
+            }
+            *samples = pos;
+            return -1;
+        };
+        // big batches: a few host threads, so that the scan hides behind the synthesis kernel
+        const int nthreads = nframes * S >= 200000 ? 4 : 1;
+        std::vector<long long> part_samples(nthreads, 0);
+        std::vector<int64_t> part_bad(nthreads, -1);
+        if (nthreads == 1) {
+            part_bad[0] = scan(0, nframes, &part_samples[0]);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthreads; t++)
+                th.emplace_back([&, t] { part_bad[t] = scan(nframes * t / nthreads, nframes * (t + 1) / nthreads, &part_samples[t]); });
+            for (std::thread &x : th) x.join();
         }
-        if (!ok) return fail(ctx, NQ_BAD_ARG, "frame %lld stream %lld: bad side info (N=%d)", (long long)(i / L.streams), (long long)(i % L.streams), f.N);
+        for (int t = 0; t < nthreads; t++)
+            if (part_bad[t] >= 0)
+                return fail(ctx, NQ_BAD_ARG, "frame %lld: bad side info (N=%d; every stream of a frame must carry the same N in {120,240,480,960}, "
+                            "periods 15..1022 where the gain is not zero, tapsets 0..2)", (long long)part_bad[t], frames[part_bad[t] * S].N);
+        if (seg_start) {   // relative -> absolute; segments that start at nframes (empty, at the end) hold everything
+            long long part_first = 0;
+            int k = 0;
+            for (int t = 0; t < nthreads; t++) {
+                const int64_t f1 = nframes * (t + 1) / nthreads;
+                for (; k < nseg && seg_start[k] < f1; k++) seg_first[k] += part_first;
+                part_first += part_samples[t];
+            }
+            for (; k < nseg; k++) seg_first[k] = part_first;
+        }
     }
     int rc = grow(ctx, &ctx->d_pframes_dev, &ctx->pframes_dev_cap, (size_t)nframes * L.streams * sizeof(PostFrame), "post side info");
     if (rc != NQ_OK) return rc;
     NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pframes_dev, frames, (size_t)nframes * L.streams * sizeof(PostFrame), cudaMemcpyHostToDevice, st));
     std::vector<PostJob> jobs;
     if (seg_start) {
-        if (nseg < 1 || seg_start[0] != 0 || seg_start[nseg] != nframes) return fail(ctx, NQ_BAD_ARG, "seg_start must run from 0 to nframes");
-        std::vector<long long> first(nframes + 1);
-        first[0] = 0;
-        for (int64_t f = 0; f < nframes; f++) first[f + 1] = first[f] + frames[f * L.streams].N;
-        for (int k = 0; k < nseg; k++) {
-            if (seg_start[k + 1] < seg_start[k]) return fail(ctx, NQ_BAD_ARG, "seg_start must be non-decreasing");
+        for (int k = 0; k < nseg; k++)
             if (seg_start[k + 1] > seg_start[k])
-                build_post_jobs(L, first[seg_start[k]], (int)seg_start[k], (int)(seg_start[k + 1] - seg_start[k]), true, false, &jobs);
-        }
+                build_post_jobs(L, seg_first[k], (int)seg_start[k], (int)(seg_start[k + 1] - seg_start[k]), true, false, &jobs);
     } else {
         build_post_jobs(L, 0, 0, (int)nframes, false, true, &jobs);
     }

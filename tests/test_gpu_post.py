@@ -172,6 +172,41 @@ def test_batch_of_many_files_reset_flag_and_segments(synth, C):
     assert np.array_equal(got, pcm.cpu().numpy())
 
 
+def test_many_segments_big_batch_threaded_side_info_scan(synth):
+    """A batch big enough for the side information to be validated on several host threads
+    (>= 200 k frames): segments of uneven lengths incl. empty ones, mixed frame sizes.  Segments are
+    independent, so the one big call must equal, bit for bit, separate calls over the two halves
+    (each below the threshold: single-threaded scan); a bad record deep inside is still caught."""
+    import torch
+    rng = np.random.default_rng(77)
+    lens = rng.integers(0, 220, 2100)
+    lens[[3, 500, 2099]] = 0
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    nframes = int(seg[-1])
+    assert nframes >= 200_000
+    fr = rand_frames(rng, nframes)
+    small = rng.uniform(size=nframes) < 0.1
+    fr["N"][small] = rng.choice([120, 240, 480], int(small.sum()))
+    first = np.concatenate([[0], np.cumsum(fr["N"])]).astype(np.int64)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    sig = (torch.rand((int(first[-1]), 2), generator=g, device="cuda") * 2 - 1) * 3000.0
+    whole = sig.clone()
+    synth.post_segments_torch(whole, fr, seg)
+    half = int(np.searchsorted(seg, nframes // 2))
+    parts = sig.clone()
+    for a, b in ((0, half), (half, len(seg) - 1)):
+        f0, f1 = int(seg[a]), int(seg[b])
+        assert f1 - f0 < 200_000
+        view = parts[int(first[f0]):int(first[f1])]
+        synth.post_segments_torch(view, fr[f0:f1], seg[a:b + 1] - seg[a])
+    torch.cuda.synchronize()
+    assert torch.equal(whole, parts)
+    bad = fr.copy()
+    bad["tapset"][nframes - 12345] = 0, 7, 0
+    with pytest.raises(nq.NqError):
+        synth.post_segments_torch(sig.clone(), bad, seg)
+
+
 def test_post_rejects_bad_side_info(synth):
     import torch
     pcm = torch.zeros((960, 2), device="cuda")
