@@ -108,7 +108,10 @@ struct nq_celt_ctx {
     float *d_hist[2] = {};
     float *d_mem[2] = {};
     int post_rows_cap = 0;
-    // ... and for the device-pointer post entry
+    // ... and for the device-pointer post entry: side information and jobs travel on a stream of
+    // their own, so that they do not queue behind the synthesis kernel the caller has just enqueued
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_ready = nullptr, side_free = nullptr;   // upload done / the post kernel that read it is done
     PostFrame *d_pframes_dev = nullptr;
     size_t pframes_dev_cap = 0;
     PostJob *d_pjobs_dev = nullptr;
@@ -456,6 +459,9 @@ int nq_celt_ctx_create(int device, nq_celt_ctx **out)
     ctx->num_sms = prop.multiProcessorCount;
     if (prepare_kernels() != cudaSuccess || prepare_post_kernel() != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    if (cudaEventCreateWithFlags(&ctx->side_ready, cudaEventDisableTiming) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
+    if (cudaEventCreateWithFlags(&ctx->side_free, cudaEventDisableTiming) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
     for (int s = 0; s < nq_celt_ctx::kSlots; s++) {
         if (cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
         if (cudaEventCreateWithFlags(&ctx->kernel_done[s], cudaEventDisableTiming) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
@@ -481,6 +487,9 @@ void nq_celt_ctx_destroy(nq_celt_ctx *ctx)
         cudaFree(ctx->d_out[s]);
         cudaFree(ctx->d_flags[s]);
     }
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->side_ready) cudaEventDestroy(ctx->side_ready);
+    if (ctx->side_free) cudaEventDestroy(ctx->side_free);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     cudaFree(ctx->d_tail[0]);
     cudaFree(ctx->d_tail[1]);
@@ -938,7 +947,9 @@ static int post_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *f
     }
     int rc = grow(ctx, &ctx->d_pframes_dev, &ctx->pframes_dev_cap, (size_t)nframes * L.streams * sizeof(PostFrame), "post side info");
     if (rc != NQ_OK) return rc;
-    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pframes_dev, frames, (size_t)nframes * L.streams * sizeof(PostFrame), cudaMemcpyHostToDevice, st));
+    // (the previous post kernel of this context may still be reading the buffers)
+    NQ_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_free, 0));
+    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pframes_dev, frames, (size_t)nframes * L.streams * sizeof(PostFrame), cudaMemcpyHostToDevice, ctx->side_stream));
     std::vector<PostJob> jobs;
     if (seg_start) {
         for (int k = 0; k < nseg; k++)
@@ -955,8 +966,12 @@ static int post_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *f
         if (cudaMalloc(&ctx->d_pjobs_dev, jobs.size() * sizeof(PostJob)) != cudaSuccess) return fail(ctx, NQ_ALLOC_FAIL, "post jobs");
         ctx->pjobs_dev_cap = (int)jobs.size();
     }
-    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pjobs_dev, jobs.data(), jobs.size() * sizeof(PostJob), cudaMemcpyHostToDevice, st));
-    return enqueue_post(ctx, L, pcm, ctx->d_pframes_dev, ctx->d_pjobs_dev, (int)jobs.size(), hist_in, mem_in, hist_out, mem_out, st);
+    NQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pjobs_dev, jobs.data(), jobs.size() * sizeof(PostJob), cudaMemcpyHostToDevice, ctx->side_stream));
+    NQ_CUDA(ctx, cudaEventRecord(ctx->side_ready, ctx->side_stream));
+    NQ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->side_ready, 0));
+    rc = enqueue_post(ctx, L, pcm, ctx->d_pframes_dev, ctx->d_pjobs_dev, (int)jobs.size(), hist_in, mem_in, hist_out, mem_out, st);
+    if (rc == NQ_OK) NQ_CUDA(ctx, cudaEventRecord(ctx->side_free, st));
+    return rc;
 }
 
 int nq_celt_post_batch_device(nq_celt_ctx *ctx, float *pcm, const nq_celt_post_frame *frames, const float *hist_in,
