@@ -70,34 +70,33 @@ __device__ __forceinline__ Taps make_taps(int T, float g, int tapset)
 //   xfade: celt.c:142-166, the filter fades from `t0` to `t1` with window^2 over the region
 //   else : celt.c:176 / pitch_sse.h:104, constant filter `t1`
 // Samples inside a block of min(T)-2 are independent of each other; blocks run in order, one
-// CTA barrier apart.  The branch structure is uniform over the CTA.
-template <int NCH>
-__device__ __forceinline__ void comb_region(PostSmem &sm, int a, int b, const Taps &t0, const Taps &t1, bool xfade, int tid)
+// CTA barrier apart.  The branch structure is uniform over the CTA; which of the two filters are
+// live is a template parameter, so that the sample loop carries no flags.
+template <int NCH, bool kXfade, bool kUse0, bool kUse1>
+__device__ __forceinline__ void comb_region_t(PostSmem &sm, int a, int b, const Taps &t0, const Taps &t1, int tid)
 {
-    const bool use0 = xfade && t0.on, use1 = t1.on;
-    if (!use0 && !use1) return;   // celt.c:126-132 and :167-173: the filter is the identity here
     int B = b - a;
-    if (use0 && t0.T - 2 < B) B = t0.T - 2;
-    if (use1 && t1.T - 2 < B) B = t1.T - 2;
+    if (kUse0 && t0.T - 2 < B) B = t0.T - 2;
+    if (kUse1 && t1.T - 2 < B) B = t1.T - 2;
     for (int i0 = a; i0 < b; i0 += B) {
         const int iend = i0 + B < b ? i0 + B : b;
         for (int i = i0 + tid; i < iend; i += kPostThreads) {
             float f = 1.f;
-            if (xfade) f = sm.win2[i - a];
+            if (kXfade) f = sm.win2[i - a];
+            const float e = 1.f - f;
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
                 float *x = sm.buf[ch] + kOff + i;
                 float acc = x[0];
-                if (use0) {
+                if (kUse0) {
                     const float *q = x - t0.T;
-                    const float e = 1.f - f;
                     acc += (e * t0.g0) * q[0];
                     acc += (e * t0.g1) * (q[1] + q[-1]);
                     acc += (e * t0.g2) * (q[2] + q[-2]);
                 }
-                if (use1) {
+                if (kUse1) {
                     const float *q = x - t1.T;
-                    if (xfade) {
+                    if (kXfade) {
                         acc += (f * t1.g0) * q[0];
                         acc += (f * t1.g1) * (q[1] + q[-1]);
                         acc += (f * t1.g2) * (q[2] + q[-2]);
@@ -113,6 +112,17 @@ __device__ __forceinline__ void comb_region(PostSmem &sm, int a, int b, const Ta
     }
 }
 
+template <int NCH>
+__device__ __forceinline__ void comb_region(PostSmem &sm, int a, int b, const Taps &t0, const Taps &t1, bool xfade, int tid)
+{
+    const bool use0 = xfade && t0.on, use1 = t1.on;
+    if (!use0 && !use1) return;   // celt.c:126-132 and :167-173: the filter is the identity here
+    if (!xfade) comb_region_t<NCH, false, false, true>(sm, a, b, t0, t1, tid);
+    else if (use0 && use1) comb_region_t<NCH, true, true, true>(sm, a, b, t0, t1, tid);
+    else if (use0) comb_region_t<NCH, true, true, false>(sm, a, b, t0, t1, tid);
+    else comb_region_t<NCH, true, false, true>(sm, a, b, t0, t1, tid);
+}
+
 // float offset of sample n (channel 0) in the staging buffer
 template <int NCH>
 __device__ __forceinline__ int stage_at(int n) { return (n >> 3) * (8 * NCH + kStagePad) + (n & 7) * NCH; }
@@ -121,14 +131,17 @@ __device__ __forceinline__ int stage_at(int n) { return (n >> 3) * (8 * NCH + kS
 // t < 120 owns samples [t*seg, (t+1)*seg), seg = N/120; the segment carries (affine maps
 // m -> m_seg + a^seg m) are combined by a warp scan plus a 4-entry hand-over between the warps.
 template <int NCH>
-__device__ __forceinline__ void deemphasis_frame(PostSmem &sm, int N, int tid, float Al8)
+__device__ __forceinline__ void deemphasis_frame(PostSmem &sm, int N, int tid, float A8, float Al8)
 {
     constexpr float a = 0.85000610f;   // mode->preemph[0], static_modes_float.h:583
     const int seg = N / kPostSegs;     // 8, 4, 2, 1
     const int lane = tid & 31, warp = tid >> 5;
     const bool act = tid < kPostSegs;
-    float A = a;                       // a^seg
-    for (int k = 1; k < seg; k <<= 1) A *= A;
+    float A = A8;                      // a^seg (20 ms frames: precomputed by the caller)
+    if (seg != 8) {
+        A = a;
+        for (int k = 1; k < seg; k <<= 1) A *= A;
+    }
     float m[NCH];
     float v[NCH][8];                   // the thread's segment (20 ms frames: 8 samples per channel, in registers)
     const bool fast = seg == 8;
@@ -179,8 +192,10 @@ __device__ __forceinline__ void deemphasis_frame(PostSmem &sm, int N, int tid, f
     }
 #pragma unroll
     for (int ch = 0; ch < NCH; ch++) {
-        float cw = 0.f;     // state entering this warp's first segment
-        for (int w = 0; w < warp; w++) cw = fmaf(A32, cw, sm.wtot[ch][w]);
+        // state entering this warp's first segment: Horner over the carries of the warps before it
+        const float w0 = sm.wtot[ch][0], w1 = sm.wtot[ch][1], w2 = sm.wtot[ch][2];
+        const float c1 = w0, c2 = fmaf(A32, c1, w1), c3 = fmaf(A32, c2, w2);
+        const float cw = warp == 0 ? 0.f : (warp == 1 ? c1 : (warp == 2 ? c2 : c3));
         const float prev = __shfl_up_sync(kFullMask, m[ch], 1);
         const float cin = lane == 0 ? cw : fmaf(Al, cw, prev);   // state entering this thread's segment
         if (tid == kPostSegs - 1) sm.mem[ch] = fmaf(Al * A, cw, m[ch]);
@@ -231,12 +246,9 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
     const PostFrame *fr = p.frames + (size_t)job.frame0 * p.frame_stride + job.stream_col;
     // (0.85000610^8)^lane: how far the de-emphasis state entering this thread's warp decays before its
     // segment of a 20 ms frame (deemphasis_frame); a chain of up to 31 dependent multiplies, done once
-    float Al8 = 1.f;
-    {
-        float A8 = 0.85000610f;
-        A8 *= A8; A8 *= A8; A8 *= A8;
-        for (int k = 0; k < (tid & 31); k++) Al8 *= A8;
-    }
+    float Al8 = 1.f, A8 = 0.85000610f;
+    A8 *= A8; A8 *= A8; A8 *= A8;
+    for (int k = 0; k < (tid & 31); k++) Al8 *= A8;
     // Plain stereo, 20 ms frames (the common case): the NEXT frame's 7680 bytes are fetched into
     // registers before the current frame is filtered, so the HBM latency hides behind the
     // recurrences instead of adding to every frame.  480 float4 = 120 threads x 4.
@@ -311,7 +323,7 @@ __device__ __forceinline__ void post_job(const PostParams &p, const PostJob &job
                 if (N > mid) comb_region<NCH>(sm, mid, N, tcur, tnew, false, tid);
             }
         }
-        deemphasis_frame<NCH>(sm, N, tid, Al8);
+        deemphasis_frame<NCH>(sm, N, tid, A8, Al8);
         // staging -> HBM, scaled to [-1, 1] (SCALEOUT, arch.h:202)
         constexpr float kScale = 1.f / 32768.f;
         if (NCH == 2 && C == 2) {
