@@ -277,8 +277,16 @@ __device__ __forceinline__ void group_store_frame(const StoreCtx &g, uint32_t ba
 // ------------------------------------------------- prefetch of the next item ---
 // TMA bulk copies of the next item's coefficient rows into ws.in (lane 0 issues, completion on
 // the warp's mbarrier).  Only once every lane is done with ws.in.
-__device__ __forceinline__ void prefetch_rows(const SynthParams &p, WarpSmem &ws, int lane, long long fnext, int cb, int rows)
+// after_generic_writes: ws.in was WRITTEN with ordinary stores since the last copy landed (a short
+// frame parks its samples there): a proxy fence orders those stores before the copy engine's writes
+// (the pattern of a TMA store after shared-memory writes: fence in every writer, barrier, one issuer).
+__device__ __forceinline__ void prefetch_rows(const SynthParams &p, WarpSmem &ws, int lane, long long fnext, int cb, int rows,
+                                              bool after_generic_writes)
 {
+    if (after_generic_writes) {   // every lane fences its own stores, then the warp meets, then lane 0 issues
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+    }
     if (lane == 0) {
         const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + cb * kFrame;
         mbar_expect_tx(&ws.bar, rows * kFrame * 4);
@@ -887,7 +895,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         };
         int nfr = (kMode == kModeMono && mono_pair(f, flag)) ? 2 : 1;
         const int state_nch = rows;   // channels with a tail of their own (kModeMono: nch is reused as frames per item)
-        prefetch_rows(p, ws, lane, f, cb, kMode == kModeMono ? nfr : rows);
+        prefetch_rows(p, ws, lane, f, cb, kMode == kModeMono ? nfr : rows, true);   // (the previous run may have ended on a short frame)
         while (f < f1) {
             if (kMode == kModeMono) nch = nfr;
             const bool more = f + nfr < f1;
@@ -920,13 +928,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                     stage1_common<kModeT>(tb, ws, lane, is_short, grp);
                     if (!is_short) {
                         // every lane has consumed its part of ws.in: the next item's rows can land while stage 2 runs
-                        if (more && !split) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch);
+                        if (more && !split) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, false);
                         long_stage2<kModeT>(p, ws, lane, off, cb, nch, store, w4, vmask);
                     } else {
                         short_stage2<kModeT>(tb, ws, lane, nch, vmask);
                         if (!split) {
                             short_output<kModeT>(p, ws, lane, off, cb, nch, store);
-                            if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch);
+                            if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, true);
                         }
                     }
                 }
@@ -935,12 +943,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                     float *col = reinterpret_cast<float *>(ws.x) + cs;
                     for (int n = lane; n < kFrame; n += 32) col[2 * n] = ws.in[park_index<kMode>(cs, n)];
                     __syncwarp();
-                    if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch);
+                    if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, true);
                 }
             } else {
                 if (kMode == kModeGroup) group_wait_plane_free(grp);
                 small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, kMode == kModeGroup ? rows : nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
-                if (more) prefetch_rows(p, ws, lane, f + 1, cb, kMode == kModeMono ? next_nfr : rows);   // ws.in fully consumed
+                if (more) prefetch_rows(p, ws, lane, f + 1, cb, kMode == kModeMono ? next_nfr : rows, true);   // ws.in fully consumed
                 const int Nf = kFrame >> sh;
                 if (kMode != kModeGroup && store) {
                     const float *plane = reinterpret_cast<const float *>(ws.x);
