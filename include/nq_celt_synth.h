@@ -66,6 +66,10 @@ NQ_API long long nq_celt_launch_count(const nq_celt_ctx *ctx);
  * for full PCIe bandwidth). */
 NQ_API void *nq_celt_host_alloc(size_t bytes);
 NQ_API void nq_celt_host_free(void *p);
+/* Experimental (tools/pcie_probe.py): kind 0 = as above, 1 = write-combined, 2 = transparent
+ * huge pages + cudaHostRegister. */
+NQ_API void *nq_celt_host_alloc_ex(size_t bytes, int kind);
+NQ_API void nq_celt_host_free_ex(void *p, size_t bytes, int kind);
 
 /* ---- batched synthesis: phase 2 of the restructured decoder ---------------
  * Replaces the per-frame call compute_inv_mdcts(mode, shortBlocks, freq,
@@ -77,9 +81,13 @@ NQ_API void nq_celt_host_free(void *p);
  *              transient frame keeps its 8 sub-blocks interleaved,
  *              freq[c*960 + j*8 + b], celt_decoder_clean.c:296)
  *   transient  [nframes]          flag byte per frame: 0 = long block, 1 = isTransient
- *              (shortBlocks = 8; celt_decoder_clean.c:586, :656).  Other bits are
- *              optional extensions, see nq_celt_synth_batch_device_ms: bits 1-2 =
- *              3 - LM (with frame_offset), bit 3 = decoder reset before the frame
+ *              (shortBlocks = 8; celt_decoder_clean.c:586, :656).  Bit 3 = decoder
+ *              reset before the frame.  These three entries take 20 ms frames
+ *              only: bits 1-2 (3 - LM) must be zero -- the _host / _host_multi
+ *              entries return NQ_BAD_ARG otherwise; _device cannot inspect device
+ *              memory and would synthesise such a frame as a 20 ms one, so frames
+ *              shorter than 20 ms go through nq_celt_synth_batch_device_ms with
+ *              frame_offset (or nq_celt_decode_batch_host, whose side info carries N)
  *   tail_in    [C][60] or NULL    raw tail left by the frame before the batch
  *              (= out_syn[c][960..1020) after that frame); NULL => zeros,
  *              i.e. a freshly reset decoder (celt_decoder_clean.c:846-859)
@@ -254,10 +262,13 @@ NQ_API void nq_celt_sink_reset(nq_celt_sink *sink);
 /* Same as _host, frames sharded contiguously over `ndev` devices (devices[i]
  * = CUDA ordinal; NULL => 0..ndev-1) with one host thread + context per
  * device and NO device-to-device traffic: a shard that starts mid-stream
- * uploads the previous frame's coefficients as its halo. */
+ * uploads the previous frame's coefficients as its halo.  The per-device
+ * contexts are created on first use and kept for the process (calls are
+ * serialised); nq_celt_multi_release() -- or cleanupCudaBuffers() -- frees them. */
 NQ_API int nq_celt_synth_batch_host_multi(const int *devices, int ndev, const float *coef,
                                           const uint8_t *transient, const float *tail_in,
                                           float *pcm_out, float *tail_out, int64_t nframes, int C);
+NQ_API void nq_celt_multi_release(void);
 
 /* ---- single-call entries with the reference's semantics -------------------
  * nq_clt_mdct_backward == clt_mdct_backward (mdct.c:267): HOST pointers,

@@ -5,6 +5,8 @@
 //   the fork's GPU seam processMDCTCuda*             cuda/mdct_cuda.hpp:79-103
 // and adds the batched phase-2 entry the restructured decoder calls once per
 // batch of frames.  No CPU fallback anywhere: every entry needs a CUDA device.
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -85,8 +87,14 @@ struct nq_celt_ctx {
     cudaEvent_t kernel_done[kSlots] = {};
     FastTables *d_fast = nullptr;
     GenericTables *d_gen = nullptr;
-    unsigned long long *d_work = nullptr;   // work counters of the dynamically scheduled launches (ring of kWorkSlots)
+    // work counters of the dynamically scheduled launches: a ring of kWorkSlots, each guarded by an
+    // event recorded behind the launch that used it last -- a launch that reuses the slot (possibly on
+    // another stream) first makes its stream wait for that event, so a counter is never zeroed while a
+    // kernel is still claiming runs from it
+    unsigned long long *d_work = nullptr;
     static constexpr int kWorkSlots = 64;
+    cudaEvent_t work_done[kWorkSlots] = {};
+    bool work_used[kWorkSlots] = {};
     int work_slot = 0;
     // scratch for the host-pointer batch entry
     float *d_in[kSlots] = {};
@@ -292,12 +300,19 @@ int enqueue_synth(nq_celt_ctx *ctx, const Layout &L, const float *coef, const ui
     if (rc == NQ_UNIMPLEMENTED)
         return fail(ctx, rc, "a channel layout needs at most %d warps (coupled streams + pairs of mono streams) and at most 30 streams with their own flags; got %d streams, %d coupled",
                     kMaxGroupStreams, L.streams, L.coupled);
+    int wslot = -1;
     if (p.nruns > resident_items(p, mode, ctx->num_sms)) {
         // one counter per launch in flight (launches on different streams may overlap)
-        p.work_counter = ctx->d_work + (ctx->work_slot++ % nq_celt_ctx::kWorkSlots);
+        wslot = ctx->work_slot++ % nq_celt_ctx::kWorkSlots;
+        p.work_counter = ctx->d_work + wslot;
+        if (ctx->work_used[wslot]) NQ_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->work_done[wslot], 0));
         NQ_CUDA(ctx, cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), stream));
     }
     NQ_CUDA(ctx, launch_synth(p, mode, ctx->num_sms, stream, nullptr));
+    if (wslot >= 0) {
+        NQ_CUDA(ctx, cudaEventRecord(ctx->work_done[wslot], stream));
+        ctx->work_used[wslot] = true;
+    }
     ctx->launches++;
     return NQ_OK;
 }
@@ -387,6 +402,38 @@ void nq_celt_host_free(void *p)
     if (p) cudaFreeHost(p);
 }
 
+// Experimental host allocators for the PCIe probe (tools/pcie_probe.py): kind 0 = cudaHostAlloc,
+// 1 = write-combined (a host->device source the CPU only ever writes), 2 = anonymous mapping
+// backed by transparent huge pages, pre-faulted, then page-locked with cudaHostRegister.
+void *nq_celt_host_alloc_ex(size_t bytes, int kind)
+{
+    void *p = nullptr;
+    if (kind == 0 || kind == 1) {
+        if (cudaHostAlloc(&p, bytes, kind == 1 ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        return p;
+    }
+    const size_t huge = (size_t)2 << 20, len = (bytes + huge - 1) / huge * huge;
+    char *raw = (char *)mmap(nullptr, len + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (raw == MAP_FAILED) return nullptr;
+    char *al = (char *)(((uintptr_t)raw + huge - 1) / huge * huge);   // (the slack stays mapped; freed by _free_ex's munmap of the aligned part only)
+    madvise(al, len, MADV_HUGEPAGE);
+    for (size_t o = 0; o < len; o += 4096) al[o] = 0;
+    if (cudaHostRegister(al, len, cudaHostRegisterDefault) != cudaSuccess) {
+        munmap(raw, len + huge);
+        return nullptr;
+    }
+    return al;
+}
+
+void nq_celt_host_free_ex(void *p, size_t bytes, int kind)
+{
+    if (!p) return;
+    if (kind == 0 || kind == 1) { cudaFreeHost(p); return; }
+    const size_t huge = (size_t)2 << 20, len = (bytes + huge - 1) / huge * huge;
+    cudaHostUnregister(p);
+    munmap(p, len);
+}
+
 int nq_celt_debug_plan(int channels, int streams, int coupled_streams, const unsigned char *mapping, int64_t nframes,
                        int num_sms, int64_t out[12])
 {
@@ -466,6 +513,8 @@ int nq_celt_ctx_create(int device, nq_celt_ctx **out)
         if (cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
         if (cudaEventCreateWithFlags(&ctx->kernel_done[s], cudaEventDisableTiming) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
     }
+    for (int s = 0; s < nq_celt_ctx::kWorkSlots; s++)
+        if (cudaEventCreateWithFlags(&ctx->work_done[s], cudaEventDisableTiming) != cudaSuccess) return bail(NQ_INTERNAL_ERROR);
     const HostTables &t = host_tables();
     if (cudaMalloc(&ctx->d_fast, sizeof(FastTables)) != cudaSuccess) return bail(NQ_ALLOC_FAIL);
     if (cudaMalloc(&ctx->d_gen, sizeof(GenericTables)) != cudaSuccess) return bail(NQ_ALLOC_FAIL);
@@ -487,6 +536,8 @@ void nq_celt_ctx_destroy(nq_celt_ctx *ctx)
         cudaFree(ctx->d_out[s]);
         cudaFree(ctx->d_flags[s]);
     }
+    for (int s = 0; s < nq_celt_ctx::kWorkSlots; s++)
+        if (ctx->work_done[s]) cudaEventDestroy(ctx->work_done[s]);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->side_ready) cudaEventDestroy(ctx->side_ready);
     if (ctx->side_free) cudaEventDestroy(ctx->side_free);
@@ -658,6 +709,32 @@ int grow(nq_celt_ctx *ctx, T **buf, size_t *cap, size_t need_bytes, const char *
     return NQ_OK;
 }
 
+// Entries without side information synthesise 20 ms frames only (rows and output slots of 960
+// samples): a flag byte that asks for a shorter frame (bits 1-2) or carries unknown bits is an error
+// there, not a silently mis-sized frame.  Returns the first offending frame or -1.
+long long first_non_20ms_flag(const uint8_t *flags, long long n)
+{
+    for (long long f = 0; f < n; f++)
+        if (flags[f] & ~(kFlagTransient | kFlagReset)) return f;
+    return -1;
+}
+
+// Tuning knobs of the host-buffer pipeline (read per call, so a probe can sweep them in one
+// process): NQ_HOST_SLOTS = chunks in flight (1..3), NQ_HOST_CHUNK_MB = megabytes of coefficients
+// per chunk.
+int host_slots()
+{
+    const char *e = getenv("NQ_HOST_SLOTS");
+    const int n = e ? atoi(e) : nq_celt_ctx::kSlots;
+    return n < 1 ? 1 : (n > nq_celt_ctx::kSlots ? nq_celt_ctx::kSlots : n);
+}
+size_t host_chunk_bytes()
+{
+    const char *e = getenv("NQ_HOST_CHUNK_MB");
+    const long mb = e ? atol(e) : 64;
+    return (size_t)(mb < 1 ? 1 : (mb > 1024 ? 1024 : mb)) << 20;
+}
+
 // Host-pointer batch over [0, nframes): chunks are pipelined H2D / synthesis (/ post stage) / D2H
 // on the context's slot streams.  `halo_coef` (+ flags): optional host halo frame of a shard that
 // starts mid-stream.  `pframes` != NULL adds the post stage (all frames must be 20 ms frames).
@@ -675,11 +752,11 @@ int host_range(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8
                float *pcm_out, long long nframes)
 {
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    constexpr int S = nq_celt_ctx::kSlots;
+    const int S = host_slots();
     const size_t in_row = (size_t)L.D * kFrame, out_row = (size_t)L.C * kFrame;
     const size_t flag_row = L.per_stream_flags ? (size_t)L.streams : 1;
     // chunk size: ~64 MB of coefficients per slot, enough frames to fill the GPU
-    long long chunk = (long long)((64u << 20) / (in_row * sizeof(float)));
+    long long chunk = (long long)(host_chunk_bytes() / (in_row * sizeof(float)));
     if (chunk < 1024) chunk = 1024;
     if (chunk > nframes) chunk = nframes;
     {
@@ -689,7 +766,7 @@ int host_range(nq_celt_ctx *ctx, const Layout &L, const float *coef, const uint8
         need = need || chunk * in_row * sizeof(float) > ctx->slot_in_cap || chunk * out_row * sizeof(float) > ctx->slot_out_cap ||
                chunk * flag_row > ctx->slot_flag_cap;
         if (need) {
-            for (int s = 0; s < S; s++) {
+            for (int s = 0; s < nq_celt_ctx::kSlots; s++) {   // (all of them: the slots beyond S must not keep a smaller buffer)
                 NQ_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
                 cudaFree(ctx->d_in[s]); cudaFree(ctx->d_out[s]); cudaFree(ctx->d_flags[s]);
                 ctx->d_in[s] = ctx->d_out[s] = nullptr; ctx->d_flags[s] = nullptr;
@@ -846,6 +923,9 @@ int nq_celt_synth_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t 
         return NQ_OK;
     }
     if (!coef || !transient || !pcm_out) return fail(ctx, NQ_BAD_ARG, "null coef/transient/pcm_out");
+    if (const long long bad = first_non_20ms_flag(transient, nframes); bad >= 0)
+        return fail(ctx, NQ_BAD_ARG, "frame %lld: flag byte 0x%02x; this entry takes 20 ms frames only (bit 0 transient, bit 3 reset); "
+                    "shorter frames need side information: nq_celt_decode_batch_host", bad, transient[bad]);
     return synth_host_range(ctx, coef, transient, tail_in, nullptr, 0, pcm_out, tail_out, nframes, C);
 }
 
@@ -1021,12 +1101,31 @@ int nq_celt_decode_batch_host(nq_celt_ctx *ctx, const float *coef, const uint8_t
             if (N != (kFrame >> ((flag >> 1) & 3)) || (flag >> 4))
                 return fail(ctx, NQ_BAD_ARG, "frame %lld stream %d: flag byte 0x%02x does not say N=%d (bit 0 transient, bits 1-2 = 3-LM, bit 3 reset)",
                             (long long)f, sidx, flag, N);
+            // offsets and sizes of a frame are taken from its first stream: every stream of a frame must agree
+            if (N != frames[f * L.streams].N)
+                return fail(ctx, NQ_BAD_ARG, "frame %lld: stream %d carries N=%d, stream 0 N=%d (a multistream packet holds one frame size)",
+                            (long long)f, sidx, N, frames[f * L.streams].N);
         }
     HostState st;
     st.tail_in = tail_in; st.tail_out = tail_out;
     st.hist_in = hist_in; st.hist_out = hist_out;
     st.mem_in = mem_in; st.mem_out = mem_out;
     return host_range(ctx, L, coef, transient, frames, st, nullptr, 0, pcm_out, nframes);
+}
+
+// Contexts of nq_celt_synth_batch_host_multi: one per device, created on first use and kept (a
+// context = streams, events, tables and ~400 MB of staging buffers; creating it per call cost more
+// than a small batch).  Calls are serialised by g_multi_mu; nq_celt_multi_release / cleanupCudaBuffers free them.
+namespace {
+std::mutex g_multi_mu;
+std::vector<nq_celt_ctx *> g_multi_ctx;   // index = position in the caller's device list (a device named twice gets two contexts)
+}
+
+void nq_celt_multi_release(void)
+{
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    for (nq_celt_ctx *c : g_multi_ctx) nq_celt_ctx_destroy(c);
+    g_multi_ctx.clear();
 }
 
 int nq_celt_synth_batch_host_multi(const int *devices, int ndev, const float *coef, const uint8_t *transient,
@@ -1041,23 +1140,33 @@ int nq_celt_synth_batch_host_multi(const int *devices, int ndev, const float *co
         return NQ_OK;
     }
     if (!coef || !transient || !pcm_out) return NQ_BAD_ARG;
+    if (const long long bad = first_non_20ms_flag(transient, nframes); bad >= 0) {
+        fprintf(stderr, "libnq_celt_b200: nq_celt_synth_batch_host_multi: frame %lld: flag byte 0x%02x; 20 ms frames only\n", bad, transient[bad]);
+        return NQ_BAD_ARG;
+    }
     if (ndev > nframes) ndev = (int)nframes;
+    std::lock_guard<std::mutex> lk(g_multi_mu);
     std::vector<int> rcs(ndev, NQ_OK);
     std::vector<std::thread> th;
     const size_t row = (size_t)C * kFrame;
+    if ((int)g_multi_ctx.size() < ndev) g_multi_ctx.resize(ndev, nullptr);
     for (int d = 0; d < ndev; d++) {
         th.emplace_back([&, d] {
-            nq_celt_ctx *ctx = nullptr;
-            int rc = nq_celt_ctx_create(devices ? devices[d] : d, &ctx);
+            const int dev = devices ? devices[d] : d;
+            nq_celt_ctx *&ctx = g_multi_ctx[d];   // (distinct elements: no two threads share one)
+            if (ctx && ctx->device != dev) {      // another device list than last time
+                nq_celt_ctx_destroy(ctx);
+                ctx = nullptr;
+            }
+            int rc = ctx ? NQ_OK : nq_celt_ctx_create(dev, &ctx);
             if (rc == NQ_OK) {
                 // contiguous, disjoint frame ranges; no collective, no peer traffic
                 const long long f0 = nframes * d / ndev, f1 = nframes * (d + 1) / ndev;
                 rc = synth_host_range(ctx, coef + f0 * row, transient + f0, f0 == 0 ? tail_in : nullptr,
-                                      f0 > 0 ? coef + (f0 - 1) * row : nullptr, f0 > 0 ? transient[f0 - 1] : 0,
+                                      f0 > 0 ? coef + (f0 - 1) * row : nullptr, f0 > 0 ? (transient[f0 - 1] & kFlagTransient) : 0,
                                       pcm_out + f0 * row, d == ndev - 1 ? tail_out : nullptr, f1 - f0, C);
-                if (rc != NQ_OK) fprintf(stderr, "libnq_celt_b200: device %d: %s\n", d, ctx->err);
+                if (rc != NQ_OK) fprintf(stderr, "libnq_celt_b200: device %d: %s\n", dev, ctx->err);
             }
-            nq_celt_ctx_destroy(ctx);
             rcs[d] = rc;
         });
     }
@@ -1259,9 +1368,12 @@ void processMDCTCudaB1C2(const float *input[2], float *output[2], const float *t
 
 void cleanupCudaBuffers(void)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    nq_celt_ctx_destroy(g_ctx);
-    g_ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        nq_celt_ctx_destroy(g_ctx);
+        g_ctx = nullptr;
+    }
+    nq_celt_multi_release();
 }
 
 void printCudaVersion(void)
