@@ -601,7 +601,7 @@ def main():
                 raise SystemExit("bench.py: the host-buffer leg and the device-resident leg disagree")
         # the platform's ceiling for exactly this traffic, measured the same way on every rank at the
         # same time (same bytes each way, same pinned buffers, raw cudaMemcpyAsync, nothing else)
-        ceil_dt_own = pcie_ceiling(torch, dev, h_coef, h_pcm, ef * 7680, max(2, args.steps // 2), barrier)
+        ceil_dt_own = pcie_ceiling(torch, dev, h_coef, h_pcm, ef * 7680, args.steps, barrier)
         ceil_dt = max_over_ranks(ceil_dt_own)
         e2e = {"value": world * ef * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": ef * (7680 + 1), "d2h_bytes_per_step": ef * 7680 + 480,

@@ -66,10 +66,6 @@ NQ_API long long nq_celt_launch_count(const nq_celt_ctx *ctx);
  * for full PCIe bandwidth). */
 NQ_API void *nq_celt_host_alloc(size_t bytes);
 NQ_API void nq_celt_host_free(void *p);
-/* Experimental (tools/pcie_probe.py): kind 0 = as above, 1 = write-combined, 2 = transparent
- * huge pages + cudaHostRegister. */
-NQ_API void *nq_celt_host_alloc_ex(size_t bytes, int kind);
-NQ_API void nq_celt_host_free_ex(void *p, size_t bytes, int kind);
 
 /* ---- batched synthesis: phase 2 of the restructured decoder ---------------
  * Replaces the per-frame call compute_inv_mdcts(mode, shortBlocks, freq,

@@ -38,7 +38,7 @@ POST_FRAME_DTYPE = np.dtype([("N", np.int32), ("pitch", np.int32, 3), ("gain", n
 
 EXPORTED_SYMBOLS = [
     "nq_celt_ctx_create", "nq_celt_ctx_destroy", "nq_celt_strerror", "nq_celt_last_error",
-    "nq_celt_device_count", "nq_celt_launch_count", "nq_celt_host_alloc", "nq_celt_host_free", "nq_celt_host_alloc_ex", "nq_celt_host_free_ex",
+    "nq_celt_device_count", "nq_celt_launch_count", "nq_celt_host_alloc", "nq_celt_host_free",
     "nq_celt_synth_batch_device", "nq_celt_synth_batch_device_ms", "nq_celt_synth_batch_host",
     "nq_celt_synth_batch_host_multi", "nq_celt_multi_release", "nq_celt_post_batch_device", "nq_celt_post_segments_device", "nq_celt_decode_batch_host",
     "nq_celt_sink_create", "nq_celt_sink_destroy", "nq_celt_sink_last_error", "nq_celt_sink_push",
@@ -81,10 +81,6 @@ def load_library():
     L.nq_celt_host_alloc.argtypes = [C.c_size_t]
     L.nq_celt_host_alloc.restype = vp
     L.nq_celt_host_free.argtypes = [vp]
-    L.nq_celt_host_alloc_ex.argtypes = [C.c_size_t, C.c_int]
-    L.nq_celt_host_alloc_ex.restype = vp
-    L.nq_celt_host_free_ex.argtypes = [vp, C.c_size_t, C.c_int]
-    L.nq_celt_host_free_ex.restype = None
     L.nq_celt_synth_batch_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int64, C.c_int, vp]
     L.nq_celt_synth_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int]
     L.nq_celt_synth_batch_device_ms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int,

@@ -5,8 +5,6 @@
 //   the fork's GPU seam processMDCTCuda*             cuda/mdct_cuda.hpp:79-103
 // and adds the batched phase-2 entry the restructured decoder calls once per
 // batch of frames.  No CPU fallback anywhere: every entry needs a CUDA device.
-#include <sys/mman.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -43,8 +41,13 @@ const HostTables &host_tables()
         // window120: modes.c:374
         for (int i = 0; i < kOverlap; i++) {
             const double s = sin(.5 * pi * (i + .5) / kOverlap);
-            t->fast.window[i] = t->gen.window[i] = (float)sin(.5 * pi * s * s);
+            t->gen.window[i] = (float)sin(.5 * pi * s * s);
         }
+        for (int h = 0; h < 2; h++)
+            for (int i = 0; i < 30; i++) {
+                const int m = 2 * i + h;
+                t->fast.wpair[h * 30 + i] = make_float2(t->gen.window[59 - m], t->gen.window[60 + m]);
+            }
         // mdct trig: mdct.c:99, argument evaluated in float (PI is a float macro)
         for (int i = 0; i <= 480; i++) t->gen.trig[i] = (float)cos(2 * 3.141592653f * i / kMdctN);
         // inter-stage twiddles with both MDCT rotations folded in
@@ -402,38 +405,6 @@ void nq_celt_host_free(void *p)
     if (p) cudaFreeHost(p);
 }
 
-// Experimental host allocators for the PCIe probe (tools/pcie_probe.py): kind 0 = cudaHostAlloc,
-// 1 = write-combined (a host->device source the CPU only ever writes), 2 = anonymous mapping
-// backed by transparent huge pages, pre-faulted, then page-locked with cudaHostRegister.
-void *nq_celt_host_alloc_ex(size_t bytes, int kind)
-{
-    void *p = nullptr;
-    if (kind == 0 || kind == 1) {
-        if (cudaHostAlloc(&p, bytes, kind == 1 ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) return nullptr;
-        return p;
-    }
-    const size_t huge = (size_t)2 << 20, len = (bytes + huge - 1) / huge * huge;
-    char *raw = (char *)mmap(nullptr, len + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-    if (raw == MAP_FAILED) return nullptr;
-    char *al = (char *)(((uintptr_t)raw + huge - 1) / huge * huge);   // (the slack stays mapped; freed by _free_ex's munmap of the aligned part only)
-    madvise(al, len, MADV_HUGEPAGE);
-    for (size_t o = 0; o < len; o += 4096) al[o] = 0;
-    if (cudaHostRegister(al, len, cudaHostRegisterDefault) != cudaSuccess) {
-        munmap(raw, len + huge);
-        return nullptr;
-    }
-    return al;
-}
-
-void nq_celt_host_free_ex(void *p, size_t bytes, int kind)
-{
-    if (!p) return;
-    if (kind == 0 || kind == 1) { cudaFreeHost(p); return; }
-    const size_t huge = (size_t)2 << 20, len = (bytes + huge - 1) / huge * huge;
-    cudaHostUnregister(p);
-    munmap(p, len);
-}
-
 int nq_celt_debug_plan(int channels, int streams, int coupled_streams, const unsigned char *mapping, int64_t nframes,
                        int num_sms, int64_t out[12])
 {
@@ -477,7 +448,7 @@ void nq_celt_debug_tables(float *t_long, float *t_short, float *window, float *t
     const HostTables &t = host_tables();
     if (t_long) memcpy(t_long, t.fast.t_long, sizeof t.fast.t_long);
     if (t_short) memcpy(t_short, t.fast.t_short, sizeof t.fast.t_short);
-    if (window) memcpy(window, t.fast.window, sizeof t.fast.window);
+    if (window) memcpy(window, t.gen.window, sizeof t.gen.window);
     if (trig) memcpy(trig, t.gen.trig, sizeof t.gen.trig);
 }
 

@@ -478,45 +478,97 @@ __device__ __forceinline__ void long_stage2(const SynthParams &p, WarpSmem &ws, 
 }
 
 // ---------------------------------------------------- short blocks, stage 2 ---
-// 8 short blocks per channel (N = 240, N2 = 120, N4 = 60).  The radix-2 step that completes the
-// 60-point transform pairs the rows r and r^1 of the transpose buffer; window + overlap-add against
-// the previous sub-block's raw tail (lane - 2, a shuffle) follow.  A ROLLED loop over k1 (the inputs
-// sit in shared memory, not in registers): a few hundred bytes of code instead of 12 KB.  The
-// finished samples wait in the channel's own -- consumed -- coefficient row, ws.in[c][0..960).
+// 8 short blocks per channel (N = 240, N2 = 120, N4 = 60).  Lane = (c, b, h).  The radix-2 step that
+// completes the 60-point transform pairs the rows r and r^1 of the transpose buffer; window +
+// overlap-add against the previous sub-block's raw tail (lane - 2, a shuffle) follow.  A ROLLED loop
+// of 30 trips (the inputs sit in shared memory, not in registers): a few hundred bytes of code.
+//
+// Trip i handles bin k1 = i in the h = 0 lanes and k1 = 29 - i in the h = 1 lanes, so that for
+// everybody the head sample is y[m] with m = 2i + h: every address of the trip (tail, window pair,
+// output) is then a lane-constant base plus a multiple of i with the same sign in all lanes, and
+// the compiler folds it into the instruction.  The transpose buffer is read "even row of the pair,
+// then odd row" (first, second) instead of "own row, partner's row": the h = 0 lanes read column i
+// while the h = 1 lanes read column 29 - i, and that way the two halves of the warp land on banks
+// of opposite parity (own-row reads would collide two ways).
+//   Y = Z * exp(j 2pi 30 h / 240) with bins k = k1 + 30 h; y[2k] = -Re Y, y[119-2k] = Im Y:
+//   h = 0: Z = first + second, head = y[2k1]    = -Re Z,        tl = y[119-2k1] = Im Z
+//   h = 1: Z = first - second, head = y[59-2k1] = Im(Z e^{jpi/4}), tl = y[60+2k1] = -Re(Z e^{jpi/4})
+// both written head = c1 Zx + c2 Zy, tl = c3 Zx + c4 Zy with lane constants.
+// Output: kModeStereo stores straight to global memory -- one shuffle with lane ^ 16 turns the
+// two samples of a trip into one {L, R} pair per lane (c = 0 keeps sample 60 + m, c = 1 sample
+// 59 - m), 16 contiguous bytes per lane pair (h = 0, 1) -- so the consumed coefficient rows are free
+// for the next frame's TMA copy as early as in a long frame.  The other modes park the finished
+// samples in the channel's own -- consumed -- coefficient row, ws.in[c][0..960), for short_output.
+// The raw tail of sub-block 7 replaces the old one in ws.tail; the old entries a group of five
+// trips needs are read before the group's first write (one warp barrier per group).
 template <int kModeT>
-__device__ __forceinline__ void short_stage2(const FastTables &tb, WarpSmem &ws, int lane, int nch, int vmask)
+__device__ __forceinline__ void short_stage2(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off, int nch,
+                                             bool store, int vmask)
 {
     constexpr bool kPaired = kModeT == kModeGroupPaired;
     constexpr int kMode = kPaired ? kModeGroup : kModeT;
+#ifndef NQ_SHORT_ST
+#define NQ_SHORT_ST 2
+#endif
+    constexpr bool kDirect = kMode == kModeStereo && NQ_SHORT_ST != 2;   // samples leave from registers
     const int c = lane >> 4, r = lane & 15, b = r >> 1, h = r & 1;
     const bool mine = !kPaired || ((vmask >> c) & 1);   // bit c = this channel is transient in this frame
-    const float2 *a_own = ws.x + c * kXChanF2 + r * kXRowF2;
-    const float2 *a_oth = ws.x + c * kXChanF2 + (r ^ 1) * kXRowF2;
-    float *stage = ws.in + park_index<kMode>(c, 120 * b);
+    // column of trip i: i (h = 0) or 29 - i (h = 1); rows: the even and the odd row of the pair.
+    // Shared-memory byte addresses that advance by a lane-constant step per trip (one add each,
+    // where indexing by the trip number costs the compiler four instructions per access).
+    uint32_t xa = smem_u32(ws.x + c * kXChanF2 + (r & ~1) * kXRowF2 + (h ? 29 : 0));
+    const uint32_t xstep = h ? (uint32_t)-8 : 8u;
+    float *st_lo = ws.in + park_index<kMode>(c, 120 * b) + 59 - h, *st_hi = st_lo + 1 + 2 * h;   // trip i: st_lo[-2i], st_hi[2i]
     // kModeMono: c = 1 is the NEXT frame of the same stream; its block 0 follows block 7 of c = 0 (lane - 2)
-    float *tail = ws.tail + (kMode == kModeMono ? 0 : c * kHalfOvl);
+    float *tail = ws.tail + (kMode == kModeMono ? 0 : c * kHalfOvl) + 59 - h;   // trip i: tail[-2i]
     const bool tail_from_smem = b == 0 && (kMode != kModeMono || c == 0);
     const bool tail_writer = b == 7 && (kMode == kModeMono ? c == nch - 1 : mine);
-    // Y = Z * exp(j 2pi 30 h / 240); y[2k] = -Re Y, y[119-2k] = Im Y with bins k = k1 + 30 h
-    //   h = 0: head = y[2k1],    tl = y[119-2k1]
-    //   h = 1: head = y[59-2k1], tl = y[60+2k1]
-    const float dr = h ? NQ_SQRT1_2 : 1.0f, di = h ? NQ_SQRT1_2 : 0.0f, sg = h ? -1.0f : 1.0f;
-#pragma unroll kShortUnroll
-    for (int k1 = 0; k1 < 30; k1++) {
-        const float2 a = a_own[k1], pa = a_oth[k1];
-        const float2 z = make_float2(fmaf(sg, a.x, pa.x), fmaf(sg, a.y, pa.y));   // h = 0: a + pa;  h = 1: pa - a
-        const float yr = fmaf(z.x, dr, -(z.y * di)), yi = fmaf(z.x, di, z.y * dr);
-        const float head = h ? yi : -yr, tl = h ? -yr : yi;
-        const int m = h ? 59 - 2 * k1 : 2 * k1;      // head = y[m]
-        float tp = __shfl_up_sync(kFull, tl, 2);     // same (c, h), sub-block b-1
-        if (tail_from_smem) tp = tail[59 - m];
-        const float wlo = tb.window[59 - m], whi = tb.window[60 + m];
-        if (mine) {
-            stage[59 - m] = fmaf(whi, tp, -(wlo * head));   // out[59-m]
-            stage[60 + m] = fmaf(wlo, tp, whi * head);      // out[60+m]
+    const float sg = h ? -1.0f : 1.0f;
+    const float c1 = h ? NQ_SQRT1_2 : -1.0f, c2 = h ? NQ_SQRT1_2 : 0.0f, c3 = h ? -NQ_SQRT1_2 : 0.0f, c4 = h ? NQ_SQRT1_2 : 1.0f;
+    const float2 *wp = tb.wpair + h * 30;
+    // direct stores: c = 0 writes {L, R}[60 + m] (ascending), c = 1 writes {L, R}[59 - m] (descending)
+    float2 *gdst = nullptr;
+    int gstep = 0;
+    if (kDirect) {
+        gdst = reinterpret_cast<float2 *>(p.pcm + off * 2) + 120 * b + (c ? 59 - h : 60 + h);
+        gstep = c ? -2 : 2;
+    }
+    constexpr int kGroup = 5;
+#pragma unroll 1
+    for (int i0 = 0; i0 < 30; i0 += kGroup) {
+        float told[kGroup];
+#pragma unroll
+        for (int k = 0; k < kGroup; k++) told[k] = tail_from_smem ? tail[-2 * k] : 0.f;
+        __syncwarp();   // the old tail entries of this group are in registers before sub-block 7 replaces them
+#pragma unroll
+        for (int k = 0; k < kGroup; k++) {
+            const float2 fa = lds_f32x2(xa), fb = lds_f32x2(xa + kXRowF2 * 8);
+            xa += xstep;
+            const float zx = fmaf(sg, fb.x, fa.x), zy = fmaf(sg, fb.y, fa.y);
+            const float head = fmaf(c2, zy, c1 * zx), tl = fmaf(c4, zy, c3 * zx);
+            float tp = __shfl_up_sync(kFull, tl, 2);     // same (c, h), sub-block b-1
+            if (tail_from_smem) tp = told[k];
+            const float2 w = wp[k];                      // (window[59-m], window[60+m])
+            const float lo = fmaf(w.y, tp, -(w.x * head));   // out[59-m]
+            const float hi = fmaf(w.x, tp, w.y * head);      // out[60+m]
+            if (kDirect) {
+                const float other = __shfl_xor_sync(kFull, c ? hi : lo, 16);
+#if NQ_SHORT_ST == 1
+                if (store) gdst[gstep * k] = c ? make_float2(other, lo) : make_float2(hi, other);
+#else
+                if (store) __stcs(gdst + gstep * k, c ? make_float2(other, lo) : make_float2(hi, other));
+#endif
+            } else if (mine) {
+                st_lo[-2 * k] = lo;
+                st_hi[2 * k] = hi;
+            }
+            if (tail_writer) tail[-2 * k] = tl;          // y_7[60 + (59-m)]
         }
-        __syncwarp();                                // the old tail entry is consumed ...
-        if (tail_writer) tail[59 - m] = tl;          // ... before block 7 replaces it: y_7[60 + (59-m)]
+        wp += kGroup;
+        tail -= 2 * kGroup;
+        st_lo -= 2 * kGroup;
+        st_hi += 2 * kGroup;
+        if (kDirect) gdst += gstep * kGroup;
     }
     __syncwarp();
 }
@@ -800,10 +852,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
     float w4[4];
     {
         const int k1 = lane < 30 ? lane : 29;
-        w4[0] = tb.window[59 - 2 * k1];
-        w4[1] = tb.window[60 + 2 * k1];
-        w4[2] = tb.window[58 - 2 * k1];
-        w4[3] = tb.window[61 + 2 * k1];
+        const float *win = p.gen->window;   // (once per kernel: global memory)
+        w4[0] = win[59 - 2 * k1];
+        w4[1] = win[60 + 2 * k1];
+        w4[2] = win[58 - 2 * k1];
+        w4[3] = win[61 + 2 * k1];
     }
 
     // Work items.  Stereo / direct: one warp per (run, channel pair).  Group: a group owns a run,
@@ -930,8 +983,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                         // every lane has consumed its part of ws.in: the next item's rows can land while stage 2 runs
                         if (more && !split) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, false);
                         long_stage2<kModeT>(p, ws, lane, off, cb, nch, store, w4, vmask);
+                    } else if (kStereo && NQ_SHORT_ST != 2) {
+                        // (samples leave from registers: ws.in is free as early as in a long frame)
+                        if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, false);
+                        short_stage2<kModeT>(p, tb, ws, lane, off, nch, store, vmask);
                     } else {
-                        short_stage2<kModeT>(tb, ws, lane, nch, vmask);
+                        short_stage2<kModeT>(p, tb, ws, lane, off, nch, store, vmask);
                         if (!split) {
                             short_output<kModeT>(p, ws, lane, off, cb, nch, store);
                             if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, true);
@@ -947,7 +1004,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                 }
             } else {
                 if (kMode == kModeGroup) group_wait_plane_free(grp);
-                small_frame_planes(p.gen, tb.window, ws.in, ws.x, ws.tail, lane, kMode == kModeGroup ? rows : nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
+                small_frame_planes(p.gen, p.gen->window, ws.in, ws.x, ws.tail, lane, kMode == kModeGroup ? rows : nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
                 if (more) prefetch_rows(p, ws, lane, f + 1, cb, kMode == kModeMono ? next_nfr : rows, true);   // ws.in fully consumed
                 const int Nf = kFrame >> sh;
                 if (kMode != kModeGroup && store) {

@@ -23,7 +23,10 @@ constexpr int kXChanF2 = 16 * kXRowF2;   // 496 float2 per channel
 struct FastTables {
     float2 t_long[kXChanF2];   // [n2][k1] (row stride 31): -(1+js)^2 e^{j2pi(n2+k1)/1920} e^{j2pi n2 k1/480}
     float2 t_short[2 * 30];    // [h][k1]:                  -(1+js)^2 e^{j2pi(h+k1)/240}  e^{j2pi h k1/60}
-    float window[kOverlap];    // static_modes_float.h:9 window120 (modes.c:374 formula)
+    // short-block mirror: wpair[h][i] = (window[59 - m], window[60 + m]) with m = 2i + h, the two
+    // window taps a lane (.., h) needs in trip i of short_stage2's loop (window120:
+    // static_modes_float.h:9, modes.c:374 formula) -- one 64-bit load per trip
+    float2 wpair[2 * 30];
 };
 
 // Tables of the generic (any shift / stride) kernel: the reference's own

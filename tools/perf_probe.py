@@ -9,6 +9,16 @@ import libnyquist_b200 as nq
 if os.environ.get("NQ_PROBE_LIB"):   # A/B runs: another build of the library
     nq.LIB_PATH = os.environ["NQ_PROBE_LIB"]
 
+def sm_clock():
+    """Current SM clock in MHz (the issue-bound variants follow it under the power cap)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        return int(pynvml.nvmlDeviceGetClockInfo(pynvml.nvmlDeviceGetHandleByIndex(0), pynvml.NVML_CLOCK_SM))
+    except Exception:
+        return None
+
+
 def run(synth, frames, C, p_tr, steps=5):
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(1)
@@ -23,11 +33,12 @@ def run(synth, frames, C, p_tr, steps=5):
     for _ in range(steps):
         synth.synth_batch_torch(coef, tr, out=pcm, want_tail=False)
     e1.record()
+    mhz = sm_clock()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     gbs = frames * C * 960 * 8 / (ms * 1e-3) / 1e9
     return dict(frames=frames, C=C, p_transient=p_tr, ms=round(ms, 3), GBps=round(gbs, 1),
-                Mframes_per_s=round(frames / ms / 1e3, 2), frac_of_6527=round(gbs / 6527.5, 3))
+                Mframes_per_s=round(frames / ms / 1e3, 2), frac_of_6527=round(gbs / 6527.5, 3), sm_mhz=mhz)
 
 def run_ms(synth, frames, streams, coupled, p_tr, steps=5):
     """Multistream layout (own transient flag per stream), identity channel mapping."""
@@ -45,11 +56,12 @@ def run_ms(synth, frames, streams, coupled, p_tr, steps=5):
     for _ in range(steps):
         synth.synth_batch_ms_torch(coef, tr, streams, coupled, list(range(D)), out=pcm, want_tail=False)
     e1.record()
+    mhz = sm_clock()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     gbs = frames * D * 960 * 8 / (ms * 1e-3) / 1e9
     return dict(frames=frames, streams=streams, coupled=coupled, p_transient=p_tr, ms=round(ms, 3), GBps=round(gbs, 1),
-                frac_of_6527=round(gbs / 6527.5, 3))
+                frac_of_6527=round(gbs / 6527.5, 3), sm_mhz=mhz)
 
 
 if __name__ == "__main__":
