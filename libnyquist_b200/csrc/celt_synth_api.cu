@@ -167,7 +167,12 @@ int fail(nq_celt_ctx *ctx, int code, const char *fmt, ...)
 // issue-bound group variants gain 0-2 %.
 constexpr long long kDynamicRun = 64;
 
-void plan_runs(long long nframes, long long resident_items, long long max_run, long long *frames_per_run, long long *nruns)
+// Dynamically claimed batches end on SHORT runs: when the work counter runs dry every warp is somewhere
+// inside its last run, so the launch's tail is half a run long on average (64 frames of one warp = 0.3 ms:
+// 1 % of a 10 M-frame launch, but 10 % of the 1.25 M frames a GPU gets when 10 M are split over eight).
+// The last half wave's worth of frames is therefore cut into runs a quarter as long.
+
+void plan_runs(long long nframes, long long resident_items, long long max_run, SynthParams *p)
 {
     long long target_runs = resident_items;
     if (target_runs < 1) target_runs = 1;
@@ -175,8 +180,17 @@ void plan_runs(long long nframes, long long resident_items, long long max_run, l
     if (K < 8) K = 8;
     if (max_run > 0 && K > max_run) K = max_run;
     if (K > nframes) K = nframes > 0 ? nframes : 1;
-    *frames_per_run = K;
-    *nruns = (nframes + K - 1) / K;
+    p->frames_per_run = K;
+    p->nruns = p->big_runs = (nframes + K - 1) / K;
+    p->small_run = K;
+    // more than ~3 waves of full-size runs (i.e. dynamically claimed): the frames of the last wave go in small runs
+    if (max_run > 0 && K == max_run && K >= 32 && nframes >= 3 * target_runs * K) {
+        const long long small_frames = target_runs * K / 2, small = K / 4;
+        p->big_runs = (nframes - small_frames) / K;
+        p->small_run = small;
+        const long long rest = nframes - p->big_runs * K;
+        p->nruns = p->big_runs + (rest + small - 1) / small;
+    }
 }
 
 // Channel layout of a batch: the arguments of opus_multistream_decoder_create
@@ -268,7 +282,7 @@ int plan_layout(const Layout &L, int num_sms, long long nframes, SynthParams *pp
     // run costs 1/kDynamicRun extra coefficient reads
     long long max_run = mode == kModeMono ? 2 * kDynamicRun : (mode == kModeDirect ? 0 : kDynamicRun);
     if (const char *e = getenv("NQ_FRAMES_PER_RUN")) max_run = atoll(e);   // tuning knob (0 = one run per resident warp)
-    plan_runs(nframes, resident, max_run, &p.frames_per_run, &p.nruns);
+    plan_runs(nframes, resident, max_run, &p);
     return NQ_OK;
 }
 

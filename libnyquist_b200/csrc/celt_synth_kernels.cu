@@ -744,8 +744,7 @@ __device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem 
     auto start_run = [&](int k) {
         if (item[k] < p.nruns) {
             seq[k]++;
-            f[k] = item[k] * p.frames_per_run;
-            f1[k] = (f[k] + p.frames_per_run < p.nframes) ? f[k] + p.frames_per_run : p.nframes;
+            run_range(p, item[k], &f[k], &f1[k]);
         } else {
             f[k] = f1[k] = 0;
             alive--;
@@ -919,8 +918,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             flag_col = p.flag_per_stream ? pair : 0;
             halo_bit = p.flag_per_stream ? (pair & 31) : 0;
         }
-        const long long f0 = run * p.frames_per_run;
-        const long long f1 = (f0 + p.frames_per_run < p.nframes) ? f0 + p.frames_per_run : p.nframes;
+        long long f0, f1;
+        run_range(p, run, &f0, &f1);
         // A run that does not open the batch (or a batch with a halo frame)
         // first re-computes the frame before it, only to obtain its raw tail.
         // ... unless the run opens on a frame that follows a decoder reset (flag bit 3: the first

@@ -76,8 +76,10 @@ struct SynthParams {
     const long long *frame_offset;     // [nframes] first sample of every frame, or nullptr: frame f starts at 960 f
     unsigned long long *work_counter;  // zeroed before the launch: runs beyond the first wave are claimed dynamically; nullptr: static
     long long nframes;
-    long long frames_per_run;
-    long long nruns;
+    long long frames_per_run;   // frames of runs [0, big_runs)
+    long long nruns;            // all runs
+    long long big_runs;         // the runs from here on hold small_run frames each: the launch ends on short runs,
+    long long small_run;        //   so the warps finish within a few frames of each other (run_range())
     int D;                      // decoded channels per frame (coefficient rows)
     int C;                      // output channels (pcm row width); == D without a channel mapping
     int npairs;                 // kModeDirect: channel pairs per frame
@@ -139,6 +141,21 @@ struct PostParams {
     int C;
     int frame_stride;        // streams
 };
+
+// Frames [*f0, *f1) of run `run`: big_runs runs of frames_per_run frames, then runs of small_run frames.
+__host__ __device__ inline void run_range(const SynthParams &p, long long run, long long *f0, long long *f1)
+{
+    long long a, len;
+    if (run < p.big_runs) {
+        a = run * p.frames_per_run;
+        len = p.frames_per_run;
+    } else {
+        a = p.big_runs * p.frames_per_run + (run - p.big_runs) * p.small_run;
+        len = p.small_run;
+    }
+    *f0 = a;
+    *f1 = a + len < p.nframes ? a + len : p.nframes;
+}
 
 size_t post_kernel_smem_bytes();
 cudaError_t prepare_post_kernel();
