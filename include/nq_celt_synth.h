@@ -247,6 +247,10 @@ NQ_API int nq_celt_sink_flush_pinned(nq_celt_sink *sink, nq_celt_ctx *ctx, const
 NQ_API int nq_celt_sink_attach(nq_celt_sink *sink, nq_celt_ctx *ctx, float *dst, int64_t skip_samples,
                                int64_t dst_samples);
 NQ_API int nq_celt_sink_finish(nq_celt_sink *sink, int64_t *decoded_samples);
+/* attach() may be given dst == NULL when the output buffer is still being allocated (zero-filling
+ * the samples of a long file takes tens of milliseconds that phase 1 can use): the worker decodes
+ * meanwhile and waits for this call before it copies the first block out.  Must come before finish(). */
+NQ_API int nq_celt_sink_set_destination(nq_celt_sink *sink, float *dst);
 /* Pinned blocks of destroyed sinks are recycled process-wide (page-locking is
  * slow); this releases them. */
 NQ_API void nq_celt_sink_trim_pool(void);
@@ -254,6 +258,9 @@ NQ_API void nq_celt_sink_trim_pool(void);
  * stream starts from a cleared decoder (tail, history, memory), wherever that
  * falls relative to the flushes. */
 NQ_API void nq_celt_sink_reset(nq_celt_sink *sink);
+/* Same for one stream: each stream of a multistream file is a decoder of its own
+ * (opus_multistream_decoder.c:237-251) and is reset on its own. */
+NQ_API void nq_celt_sink_reset_stream(nq_celt_sink *sink, int stream);
 
 /* Same as _host, frames sharded contiguously over `ndev` devices (devices[i]
  * = CUDA ordinal; NULL => 0..ndev-1) with one host thread + context per

@@ -80,7 +80,16 @@ static const int OPUS_SAMPLE_RATE = 48000;
 
 namespace {
 
-thread_local double g_last_timing[3] = {0, 0, 0};   // phase 1, phase 2, trim/gain (seconds) of this thread's last Load
+// Time budget of this thread's last Load, seconds: [0] phase 1 (the op_read_float loop: entropy decode
+// on the CPU), [1] phase 2 tail (what is left of the GPU work when phase 1 ends), [2] gain / SILK sum,
+// [3] op_test_memory + op_test_open + header, [4] waiting for the zero-filled AudioData.samples (the
+// resize runs on a helper thread next to phase 1), [5] context lease + sink + attach, [6] whole
+// constructor, [7] the resize itself (overlapped)
+thread_local double g_last_timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+struct OpusFileCloser {
+    void operator()(OggOpusFile *f) const { if (f) op_free(f); }
+};
 
 // A context is not re-entrant (nq_celt_synth.h), but nqr::NyquistIO::Load may be called from
 // several threads at once, as the reference's can: every Load leases a context of its own from a
@@ -278,43 +287,57 @@ int phase1_threads(int streams)
 
 }  // namespace
 
-extern "C" void nq_twophase_last_timing(double out[3]) { memcpy(out, g_last_timing, sizeof g_last_timing); }
+extern "C" void nq_twophase_last_timing(double out[8]) { memcpy(out, g_last_timing, sizeof g_last_timing); }
 
 class OpusDecoderInternal
 {
 public:
     OpusDecoderInternal(AudioData *d, const std::vector<uint8_t> &fileData) : d(d)
     {
+        const double tc0 = now_s();
         int err;
-        fileHandle = op_test_memory(fileData.data(), fileData.size(), &err);
+        // (owned from here on: a refused or failed file must not leak the OggOpusFile)
+        fileHandle.reset(op_test_memory(fileData.data(), fileData.size(), &err));
         if (!fileHandle) throw std::runtime_error("File is not a valid ogg vorbis file");
-        if (op_test_open(fileHandle) != 0) {
-            fileHandle = nullptr;   // op_test_open frees it on failure
+        if (op_test_open(fileHandle.get()) != 0) {
+            fileHandle.release();   // op_test_open frees it on failure
             throw std::runtime_error("Could not open file");
         }
-        const OpusHead *header = op_head(fileHandle, 0);
+        const OpusHead *header = op_head(fileHandle.get(), 0);
 
         d->sampleRate = OPUS_SAMPLE_RATE;
         d->channelCount = (uint32_t)header->channel_count;
         d->sourceFormat = MakeFormatForBits(32, true, false);
-        const int64_t totalSamples = op_pcm_total(fileHandle, -1);   // samples in a single channel
+        const int64_t totalSamples = op_pcm_total(fileHandle.get(), -1);   // samples in a single channel
         d->lengthSeconds = double(uint64_t(totalSamples / OPUS_SAMPLE_RATE));
         d->frameSize = (uint32_t)header->channel_count * GetFormatBitsPerSample(d->sourceFormat);
-        d->samples.resize(size_t(totalSamples) * d->channelCount);
-
-        if (op_link_count(fileHandle) != 1)
+        if (op_link_count(fileHandle.get()) != 1)
             throw std::runtime_error("two-phase Opus decoder: chained Ogg Opus streams are not supported");
-        if (!decodeTwoPhase(header, totalSamples)) throw std::runtime_error("could not read any data");
-    }
-
-    ~OpusDecoderInternal()
-    {
-        if (fileHandle) op_free(fileHandle);
+        // samples.resize() zero-fills (86 MB for the bundled 224 s stereo file: tens of milliseconds of
+        // page faults); phase 1 does not need the buffer until its first block of 2048 frames is
+        // through phase 2, so the resize runs on a helper thread meanwhile
+        double resizeSeconds = 0;
+        std::thread resizer([&] {
+            const double r0 = now_s();
+            d->samples.resize(size_t(totalSamples) * d->channelCount);
+            resizeSeconds = now_s() - r0;
+            resizerDone.store(true);
+        });
+        struct Joiner {
+            std::thread &t;
+            ~Joiner() { if (t.joinable()) t.join(); }
+        } joinResizer{resizer};
+        g_last_timing[3] = now_s() - tc0;
+        const bool ok = decodeTwoPhase(header, totalSamples, resizer);
+        g_last_timing[6] = now_s() - tc0;
+        g_last_timing[7] = resizeSeconds;
+        if (!ok) throw std::runtime_error("could not read any data");
     }
 
 private:
-    bool decodeTwoPhase(const OpusHead *header, int64_t totalSamples)
+    bool decodeTwoPhase(const OpusHead *header, int64_t totalSamples, std::thread &resizer)
     {
+        const double ts0 = now_s();
         const int ch = d->channelCount;
         ContextLease ctx;   // (declared before the sink: the sink's worker thread uses it until the sink is destroyed)
         SinkHolder sink;
@@ -326,10 +349,20 @@ private:
         // positional window opusfile applies: pre_skip samples dropped at the head, the end trimmed
         // to the final granule position (opusfile.c:2673-2721) ----
         const int64_t preSkip = header->pre_skip;
-        float *out = d->samples.data();
-        if (nq_celt_sink_attach(sink.s, ctx.get(), out, preSkip, totalSamples) != NQ_OK)
+        // (destination announced below, when the zero-filled samples exist)
+        if (nq_celt_sink_attach(sink.s, ctx.get(), nullptr, preSkip, totalSamples) != NQ_OK)
             throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(sink.s));
         const double t0 = now_s();
+        g_last_timing[5] = t0 - ts0;
+        bool haveOut = false;
+        auto announceOut = [&] {
+            if (haveOut) return;
+            const double w0 = now_s();
+            resizer.join();
+            g_last_timing[4] = now_s() - w0;
+            if (totalSamples > 0) nq_celt_sink_set_destination(sink.s, d->samples.data());
+            haveOut = true;
+        };
         std::vector<float> placeholder(size_t(5760) * ch);   // 120 ms, the largest Opus packet
         std::vector<float> cpuPcm;   // phase-1 PCM while no CELT frame has turned up: the output of a SILK-only file
         int64_t framesRead = 0;
@@ -345,10 +378,11 @@ private:
             pp.pcm.assign(pp.streams, std::vector<float>(size_t(5760) * 2));
             pp.items.resize(pp.streams);
             pp.pool.reset(new StreamPool(nthreads - 1));
-            op_set_decode_callback(fileHandle, parallel_decode_cb, &pp);
+            op_set_decode_callback(fileHandle.get(), parallel_decode_cb, &pp);
         }
         for (;;) {
-            const int n = op_read_float(fileHandle, placeholder.data(), (int)placeholder.size(), nullptr);
+            const int n = op_read_float(fileHandle.get(), placeholder.data(), (int)placeholder.size(), nullptr);
+            if (!haveOut && resizerDone.load()) announceOut();
             if (n == 0) break;   // EOF
             if (n < 0) {
                 std::cerr << "Opus decode error: " << n << std::endl;
@@ -359,10 +393,12 @@ private:
             if (nq_phase1_frames_so_far() == 0 || nq_phase1_saw_silk_so_far()) cpuPcm.insert(cpuPcm.end(), placeholder.begin(), placeholder.begin() + size_t(n) * ch);
             else if (!cpuPcm.empty()) std::vector<float>().swap(cpuPcm);
         }
-        op_set_decode_callback(fileHandle, nullptr, nullptr);
+        op_set_decode_callback(fileHandle.get(), nullptr, nullptr);
         pp.pool.reset();   // helpers joined before the session goes away
         const nq_phase1_stats st = nq_phase1_end();
         const double t1 = now_s();
+        announceOut();
+        float *out = d->samples.data();
 
         // ---- phase 2, the rest: last partial block + wait for the worker ----
         int64_t decoded = 0;
@@ -414,7 +450,8 @@ private:
     }
 
     NO_MOVE(OpusDecoderInternal);
-    OggOpusFile *fileHandle = nullptr;
+    std::unique_ptr<OggOpusFile, OpusFileCloser> fileHandle;
+    std::atomic<bool> resizerDone{false};
     AudioData *d;
 };
 

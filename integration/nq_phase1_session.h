@@ -9,6 +9,7 @@ struct nq_phase1_stats {
     int mode_switch;      // consecutive packets of different coding modes (redundancy frames, cross-fades, resets)
     int irregular_celt;   // celt_decode_with_ec without packet data (concealment) or for less than 10 ms next to SILK
     int error;            // first nq_celt_sink_push error, or 0
+    int resets;           // OPUS_RESET_STATE of a CELT decoder that had decoded frames before
 };
 
 // One decode session per calling thread: the loader brackets its op_read_float loop with these.

@@ -19,6 +19,7 @@ struct nq_phase1_session {
     std::atomic<bool> silk{false}, mode_switch{false}, lost_celt{false}, short_celt{false};
     std::atomic<int> error{0};
     std::atomic<long long> frames{0};
+    std::atomic<int> resets{0};
 };
 
 namespace {
@@ -55,6 +56,7 @@ nq_phase1_stats nq_phase1_end(void)
         // (a CELT-only file may hold 2.5 / 5 ms frames of its own; next to SILK such calls are the mode-switch frames)
         st.irregular_celt = (s->lost_celt.load() || (s->silk.load() && s->short_celt.load())) ? 1 : 0;
         st.error = s->error.load();
+        st.resets = s->resets.load();
         delete s;
     }
     g_t = ThreadState();
@@ -76,6 +78,23 @@ void nq_phase1_bind(nq_phase1_session *session, int stream)
         int seen = session->max_bound.load();
         while (stream > seen && !session->max_bound.compare_exchange_weak(seen, stream)) {}
     }
+}
+
+// OPUS_RESET_STATE -> nq_celt_sink_reset_stream.  A decoder the session has not seen a frame from
+// yet (its initialisation, or a reset before its first frame) needs nothing: a stream's first
+// frame starts from a cleared state anyway.
+extern "C" void nq_phase1_reset_tap(const void *dec)
+{
+    ThreadState &t = g_t;
+    nq_phase1_session *s = t.session;
+    if (!s || !s->sink) return;
+    int stream = t.stream;
+    if (stream < 0)
+        for (size_t i = 0; i < s->decoders.size(); i++)
+            if (s->decoders[i] == dec) stream = (int)i;
+    if (stream < 0) return;
+    nq_celt_sink_reset_stream(s->sink, stream);
+    s->resets.fetch_add(1);
 }
 
 extern "C" void nq_phase1_note_silk(int mode, int prev_mode)

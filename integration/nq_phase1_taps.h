@@ -12,6 +12,9 @@ extern "C" {
  * active sink when its last channel-0 call arrives. */
 void nq_phase1_frame_tap(const void *celt_decoder, const float *freq, int CC, int N, int LM, int shortBlocks, int c,
                          int T0, int T1, float g0, float g1, int tapset0, int tapset1);
+/* The CELT decoder state `celt_decoder` is being cleared: OPUS_RESET_STATE (celt_decoder_clean.c:846-859)
+ * or its initialisation (:137).  The stream's next frame starts from a reset decoder. */
+void nq_phase1_reset_tap(const void *celt_decoder);
 /* silk_Decode is about to run for a packet of coding mode `mode` (MODE_SILK_ONLY 1000 / MODE_HYBRID
  * 1001), the previous packet's having been `prev_mode` (0: none yet). */
 void nq_phase1_note_silk(int mode, int prev_mode);

@@ -1,30 +1,41 @@
 // C entry for tests and the bench: nqr::NyquistIO::Load (the reference's own Common.cpp, unmodified)
-// on top of the two-phase OpusDecoder.  ctypes cannot call C++ directly.
+// on top of the two-phase OpusDecoder.  ctypes cannot call C++ directly.  The samples are handed out
+// in place (the AudioData lives until nq_twophase_free): copying 86 MB out of the vector would be a
+// cost of this wrapper, not of Load.
 #include "Decoders.h"
 
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+
+namespace {
+std::mutex g_mu;
+std::map<const float *, std::unique_ptr<nqr::AudioData>> g_live;
+}
 
 extern "C" {
 
-extern void nq_twophase_last_timing(double out[3]);
+extern void nq_twophase_last_timing(double out[8]);
 
-// Returns 0 and a malloc'ed interleaved float buffer the caller frees with nq_twophase_free;
-// -1 and a message on stderr if Load throws.
+// Returns 0 and the interleaved float samples (valid until nq_twophase_free); -1 and a message on
+// stderr if Load throws.  timing: 8 doubles, see OpusDecoderTwoPhase.cpp.
 __attribute__((visibility("default"))) int nq_twophase_load(const char *path, float **samples, size_t *count,
-                                                             int *channels, int *sample_rate, double timing[3])
+                                                             int *channels, int *sample_rate, double timing[8])
 {
     try {
         nqr::NyquistIO loader;
-        nqr::AudioData data;
-        loader.Load(&data, std::string(path));
-        *count = data.samples.size();
-        *channels = data.channelCount;
-        *sample_rate = data.sampleRate;
-        *samples = (float *)malloc(sizeof(float) * data.samples.size());
-        memcpy(*samples, data.samples.data(), sizeof(float) * data.samples.size());
+        std::unique_ptr<nqr::AudioData> data(new nqr::AudioData());
+        loader.Load(data.get(), std::string(path));
+        *count = data->samples.size();
+        *channels = data->channelCount;
+        *sample_rate = data->sampleRate;
+        *samples = data->samples.data();
         if (timing) nq_twophase_last_timing(timing);
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_live[data->samples.data()] = std::move(data);
         return 0;
     } catch (const std::exception &e) {
         std::cerr << "nq_twophase_load: " << e.what() << std::endl;
@@ -32,6 +43,10 @@ __attribute__((visibility("default"))) int nq_twophase_load(const char *path, fl
     }
 }
 
-__attribute__((visibility("default"))) void nq_twophase_free(float *p) { free(p); }
+__attribute__((visibility("default"))) void nq_twophase_free(float *p)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_live.erase(p);
+}
 
 }  // extern "C"

@@ -242,9 +242,19 @@ void worker_main(nq_celt_sink *s)
                 long long a = s->produced, b = s->produced + n;
                 long long lo = a > s->skip ? a : s->skip;
                 long long hi = b < s->skip + s->dst_samples ? b : s->skip + s->dst_samples;
-                if (hi > lo)
-                    memcpy(s->dst + (size_t)(lo - s->skip) * s->channels, s->out + (size_t)(lo - a) * s->channels,
-                           sizeof(float) * (size_t)(hi - lo) * s->channels);
+                if (hi > lo) {
+                    float *dst;
+                    {   // the destination may be announced after the attach (nq_celt_sink_set_destination)
+                        std::unique_lock<std::mutex> lk(s->mu);
+                        s->cv.wait(lk, [&] { return s->dst != nullptr || s->stop; });
+                        dst = s->dst;
+                    }
+                    if (dst)
+                        memcpy(dst + (size_t)(lo - s->skip) * s->channels, s->out + (size_t)(lo - a) * s->channels,
+                               sizeof(float) * (size_t)(hi - lo) * s->channels);
+                    else
+                        rc = sink_fail(s, NQ_INVALID_STATE, "finished without a destination");
+                }
                 s->produced = b;
             }
         }
@@ -347,8 +357,11 @@ int nq_celt_sink_push(nq_celt_sink *s, int stream, const float *freq, int CC, in
     long long f;
     size_t fi;
     Block b;
+    bool after_reset;
     {
         std::lock_guard<std::mutex> lk(s->push_mu);
+        after_reset = s->reset_next[stream] != 0;
+        s->reset_next[stream] = 0;
         f = s->pushed[stream];
         const size_t k = (size_t)(f / kBlockFrames - s->first_block);
         fi = (size_t)(f % kBlockFrames);
@@ -359,8 +372,7 @@ int nq_celt_sink_push(nq_celt_sink *s, int stream, const float *freq, int CC, in
     for (int c = 0; c < nch; c++)   // rows keep the 960-float stride whatever the frame size
         memcpy(b.coef + (fi * s->D + row + c) * kFrame, freq + (size_t)c * N, sizeof(float) * N);
     // a frame with one short block IS a long block of the same size (celt_decoder_clean.c:273-284)
-    b.flags[fi * s->streams + stream] = (uint8_t)((shortBlocks > 1 ? 1 : 0) | ((3 - LM) << 1) | (s->reset_next[stream] ? 8 : 0));
-    s->reset_next[stream] = 0;
+    b.flags[fi * s->streams + stream] = (uint8_t)((shortBlocks > 1 ? 1 : 0) | ((3 - LM) << 1) | (after_reset ? 8 : 0));
     b.post[fi * s->streams + stream] = *post;
     std::lock_guard<std::mutex> lk(s->push_mu);
     s->pushed[stream] = f + 1;
@@ -404,7 +416,15 @@ void nq_celt_sink_reset(nq_celt_sink *s)
     // OPUS_RESET_STATE, celt_decoder_clean.c:846-859: decode_mem, preemph_memD cleared.  Frames
     // already pushed keep their state; the NEXT frame of every stream carries the reset flag, so a
     // reset may fall anywhere between two pushes (phase 2 zeroes tail / history / memory there).
+    std::lock_guard<std::mutex> lk(s->push_mu);
     std::fill(s->reset_next.begin(), s->reset_next.end(), 1);
+}
+
+void nq_celt_sink_reset_stream(nq_celt_sink *s, int stream)
+{
+    if (!s || stream < 0 || stream >= s->streams) return;
+    std::lock_guard<std::mutex> lk(s->push_mu);
+    s->reset_next[stream] = 1;
 }
 
 int nq_celt_sink_flush(nq_celt_sink *s, nq_celt_ctx *ctx, float *pcm_out, int64_t capacity_samples, int64_t *nsamples)
@@ -449,9 +469,23 @@ int nq_celt_sink_flush_pinned(nq_celt_sink *s, nq_celt_ctx *ctx, const float **p
     return rc;
 }
 
+int nq_celt_sink_set_destination(nq_celt_sink *s, float *dst)
+{
+    if (!s || !dst) return NQ_BAD_ARG;
+    if (!s->ctx) return sink_fail(s, NQ_INVALID_STATE, "sink is not in streaming mode");
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->dst = dst;
+    }
+    s->cv.notify_all();
+    return NQ_OK;
+}
+
 int nq_celt_sink_attach(nq_celt_sink *s, nq_celt_ctx *ctx, float *dst, int64_t skip_samples, int64_t dst_samples)
 {
-    if (!s || !ctx || skip_samples < 0 || dst_samples < 0 || (dst_samples > 0 && !dst)) return NQ_BAD_ARG;
+    // (dst == NULL with dst_samples > 0: the destination follows with nq_celt_sink_set_destination; the
+    // worker decodes meanwhile and waits for it before it copies the first block out)
+    if (!s || !ctx || skip_samples < 0 || dst_samples < 0) return NQ_BAD_ARG;
     if (s->ctx) return sink_fail(s, NQ_INVALID_STATE, "sink already attached");
     if (min_pushed(s) != 0) return sink_fail(s, NQ_INVALID_STATE, "attach before the first push (or after a flush)");
     s->ctx = ctx;

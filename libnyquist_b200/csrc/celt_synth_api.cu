@@ -645,19 +645,39 @@ void build_post_jobs(const Layout &L, long long sample0, int frame0, int nframes
 }
 
 // Post jobs of frames [0, n) of a (chunk of a) batch whose flag bytes `flags` (host, one record of
-// `fcols` bytes per frame, column 0 examined) may carry kFlagReset: every reset starts a new piece
-// with its own CTAs and a zeroed filter state; the first piece continues from the incoming state
-// unless it opens on a reset; only the last piece leaves its state behind.
+// `fcols` bytes per frame) may carry kFlagReset: a reset starts a new piece with its own CTA and a
+// zeroed filter state.  Every stream is a decoder of its own and is reset on its own, so each
+// channel job is cut at the resets of ITS stream (column stream_col; column 0 without per-stream
+// flags).  The first piece continues from the incoming state unless it opens on a reset; only the
+// last piece leaves its state behind.
 void build_post_jobs_with_resets(const Layout &L, const uint8_t *flags, int fcols, const nq_celt_post_frame *frames,
                                  long long n, std::vector<PostJob> *jobs)
 {
-    long long start = 0, sample0 = 0, pos = 0;
-    for (long long f = 1; f <= n; f++) {
-        pos += frames[(f - 1) * L.streams].N;
-        if (f == n || (flags[f * fcols] & kFlagReset)) {
-            build_post_jobs(L, sample0, (int)start, (int)(f - start), (flags[start * fcols] & kFlagReset) != 0, f == n, jobs);
-            start = f;
-            sample0 = pos;
+    std::vector<PostJob> whole;
+    build_post_jobs(L, 0, 0, (int)n, false, true, &whole);
+    bool any_reset = false;
+    for (long long f = 0; f < n && !any_reset; f++)
+        for (int c = 0; c < fcols && !any_reset; c++) any_reset = (flags[f * fcols + c] & kFlagReset) != 0;
+    if (!any_reset) {
+        jobs->insert(jobs->end(), whole.begin(), whole.end());
+        return;
+    }
+    std::vector<long long> first(n + 1, 0);   // first sample of every frame
+    for (long long f = 0; f < n; f++) first[f + 1] = first[f] + frames[f * L.streams].N;
+    for (const PostJob &w : whole) {
+        const int col = fcols > 1 ? w.stream_col : 0;
+        long long start = 0;
+        for (long long f = 1; f <= n; f++) {
+            if (f == n || (flags[f * fcols + col] & kFlagReset)) {
+                PostJob j = w;
+                j.sample0 = first[start];
+                j.frame0 = (int)start;
+                j.nframes = (int)(f - start);
+                j.reset = (flags[start * fcols + col] & kFlagReset) ? 1 : 0;
+                j.write_state = f == n ? 1 : 0;
+                jobs->push_back(j);
+                start = f;
+            }
         }
     }
 }

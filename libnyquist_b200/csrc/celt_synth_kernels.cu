@@ -924,7 +924,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         // first re-computes the frame before it, only to obtain its raw tail.
         // ... unless the run opens on a frame that follows a decoder reset (flag bit 3: the first
         // frame of another file in a batch of many): its tail is zero by definition.
-        const bool warm = (f0 > 0 || p.halo_coef != nullptr) && !(p.transient[f0 * p.flag_stride + flag_col] & kFlagReset);
+        bool opens_on_reset = (p.transient[f0 * p.flag_stride + flag_col] & kFlagReset) != 0;
+        if (kPaired && flag_col1 >= 0)   // (two streams in this warp: both must have been reset)
+            opens_on_reset = opens_on_reset && (p.transient[f0 * p.flag_stride + flag_col1] & kFlagReset) != 0;
+        const bool warm = (f0 > 0 || p.halo_coef != nullptr) && !opens_on_reset;
         for (int i = lane; i < 2 * kHalfOvl; i += 32) {
             const int ch = i / kHalfOvl;
             float t = 0.f;
@@ -939,7 +942,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         // transient bit of the second channel when it is a stream of its own
         int tr1 = -1;
         if (kPaired && flag_col1 >= 0)
-            tr1 = f < 0 ? (p.halo_transient >> flag_col1) & 1 : p.transient[f * p.flag_stride + flag_col1] & 1;
+            tr1 = f < 0 ? (p.halo_transient >> flag_col1) & 1 : p.transient[f * p.flag_stride + flag_col1] & (kFlagTransient | kFlagReset);
         // kModeMono: an item is one frame, or two consecutive 20 ms frames of the same block type
         // (never the warm-up frame, whose output is not stored); nfr = frames of the current item
         auto mono_pair = [&](long long g, int gflag) -> bool {
@@ -954,11 +957,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             const int next_flag = more ? flags[(f + nfr) * p.flag_stride] : 0;
             const int next_nfr = (kMode == kModeMono && more && mono_pair(f + nfr, next_flag)) ? 2 : 1;
             int next_tr1 = -1;
-            if (kPaired && flag_col1 >= 0 && more) next_tr1 = p.transient[(f + 1) * p.flag_stride + flag_col1] & 1;
-            if (flag & kFlagReset) {   // OPUS_RESET_STATE before this frame (celt_decoder_clean.c:846-859)
-                for (int i = lane; i < 2 * kHalfOvl; i += 32) ws.tail[i] = 0.f;
+            if (kPaired && flag_col1 >= 0 && more) next_tr1 = p.transient[(f + 1) * p.flag_stride + flag_col1] & (kFlagTransient | kFlagReset);
+            // OPUS_RESET_STATE before this frame (celt_decoder_clean.c:846-859); two mono streams that share a
+            // warp are decoders of their own: tr1 carries the second one's reset bit next to its transient bit
+            const bool reset0 = (flag & kFlagReset) != 0, reset1 = kPaired && tr1 >= 0 ? (tr1 & kFlagReset) != 0 : reset0;
+            if (reset0 || reset1) {
+                for (int i = lane; i < 2 * kHalfOvl; i += 32)
+                    if (i < kHalfOvl ? reset0 : reset1) ws.tail[i] = 0.f;
                 __syncwarp();
             }
+            if (kPaired && tr1 >= 0) tr1 &= kFlagTransient;
             while (!mbar_try_wait(&ws.bar, phase)) {}
             phase ^= 1;
             const bool store = f >= f0;

@@ -8,6 +8,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+
+namespace {
+std::mutex g_mu;
+std::map<const float *, std::unique_ptr<nqr::AudioData>> g_live;   // samples handed out in place: no copy inside the timed call
+}
 
 extern "C" {
 
@@ -16,13 +24,14 @@ __attribute__((visibility("default"))) int nqref_load(const char *path, float **
 {
     try {
         nqr::NyquistIO loader;
-        nqr::AudioData data;
-        loader.Load(&data, std::string(path));
-        *count = data.samples.size();
-        *channels = data.channelCount;
-        *sample_rate = data.sampleRate;
-        *samples = (float *)malloc(sizeof(float) * data.samples.size());
-        memcpy(*samples, data.samples.data(), sizeof(float) * data.samples.size());
+        std::unique_ptr<nqr::AudioData> data(new nqr::AudioData());
+        loader.Load(data.get(), std::string(path));
+        *count = data->samples.size();
+        *channels = data->channelCount;
+        *sample_rate = data->sampleRate;
+        *samples = data->samples.data();
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_live[data->samples.data()] = std::move(data);
         return 0;
     } catch (const std::exception &e) {
         std::cerr << "nqref_load: " << e.what() << std::endl;
@@ -30,6 +39,10 @@ __attribute__((visibility("default"))) int nqref_load(const char *path, float **
     }
 }
 
-__attribute__((visibility("default"))) void nqref_free(float *p) { free(p); }
+__attribute__((visibility("default"))) void nqref_free(float *p)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_live.erase(p);
+}
 
 }  // extern "C"

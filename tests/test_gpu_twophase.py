@@ -37,7 +37,7 @@ def twophase():
 def load(L, path):
     p = C.POINTER(C.c_float)()
     n, ch, sr = C.c_size_t(0), C.c_int(0), C.c_int(0)
-    tm = (C.c_double * 3)()
+    tm = (C.c_double * 8)()
     t0 = time.perf_counter()
     rc = L.nq_twophase_load(path.encode(), C.byref(p), C.byref(n), C.byref(ch), C.byref(sr), tm)
     wall = time.perf_counter() - t0
