@@ -367,6 +367,39 @@ def extras(torch, np, nq, synth, dev, peak, with_cpu_baseline):
                     what="nqr::NyquistIO::Load, 7.1 multistream file (3 coupled + 2 mono streams, BASELINE.json configs[3]); "
                          "phase 1 decodes the five streams of a packet in parallel",
                     **timed_load(path8, 5))
+            # many files at once: nqr::LoadOpusBatch (phase 1 on one host thread per file, ONE synthesis +
+            # ONE post launch for all of them) next to K loads of the unmodified reference on K threads
+            try:
+                K = min(os.cpu_count() or 1, 16)
+                L.nq_twophase_load_batch.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
+                                                     C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+                arr = (C.c_char_p * K)(*[path.encode()] * K)
+                best = None
+                for _ in range(3):
+                    ptrs, counts, chans, st = (C.POINTER(C.c_float) * K)(), (C.c_size_t * K)(), (C.c_int * K)(), (C.c_double * 7)()
+                    t0 = time.perf_counter()
+                    rc = L.nq_twophase_load_batch(arr, K, K, ptrs, counts, chans, st)
+                    dt = time.perf_counter() - t0
+                    assert rc == 0
+                    first = np.ctypeslib.as_array(ptrs[0], shape=(counts[0],)).copy()
+                    for i in range(K):
+                        L.nq_twophase_free(ptrs[i])
+                    if best is None or dt < best[0]:
+                        best = (dt, list(st))
+                R = C.CDLL(ref.LOAD_LIB_PATH)
+                R.nqref_load_many.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int]
+                R.nqref_load_many.restype = C.c_double
+                ref_dt = min(R.nqref_load_many(arr, K, K) for _ in range(2))
+                want1, _, _ = ref.nyquist_load(path)
+                out["file_decode_batch"] = {
+                    "what": f"nqr::LoadOpusBatch of {K} x sb-reverie.opus: phase 1 on {K} host threads, then ONE synthesis launch + ONE post "
+                            f"launch over all files; next to {K} loads of the unmodified reference on {K} threads of the same host",
+                    "files": K, "two_phase_ms": best[0] * 1e3, "phase1_ms": best[1][0] * 1e3, "phase2_ms": best[1][1] * 1e3,
+                    "kernel_launches": int(best[1][6]), "frames": int(best[1][5]), "files_per_s": K / best[0],
+                    "reference_ms": ref_dt * 1e3, "reference_files_per_s": K / ref_dt, "speedup": ref_dt / best[0],
+                    "max_abs_pcm_err": float(np.abs(first - want1.ravel()).max())}
+            except Exception as e:
+                out["file_decode_batch_error"] = repr(e)
     except Exception as e:   # informational leg: never fail the bench line
         out["file_decode_error"] = repr(e)
     return out

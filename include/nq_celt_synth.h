@@ -59,6 +59,10 @@ NQ_API void nq_celt_ctx_destroy(nq_celt_ctx *ctx);
 NQ_API const char *nq_celt_strerror(int code);
 NQ_API const char *nq_celt_last_error(const nq_celt_ctx *ctx);
 NQ_API int nq_celt_device_count(void);
+/* The context's device ordinal and its own stream (a cudaStream_t), for callers that enqueue copies
+ * next to the batch entries. */
+NQ_API int nq_celt_ctx_device(const nq_celt_ctx *ctx);
+NQ_API void *nq_celt_ctx_stream(const nq_celt_ctx *ctx);
 /* Number of kernel launches issued through this context so far. */
 NQ_API long long nq_celt_launch_count(const nq_celt_ctx *ctx);
 
@@ -254,6 +258,24 @@ NQ_API int nq_celt_sink_set_destination(nq_celt_sink *sink, float *dst);
 /* Pinned blocks of destroyed sinks are recycled process-wide (page-locking is
  * slow); this releases them. */
 NQ_API void nq_celt_sink_trim_pool(void);
+/* Phase 2 for MANY files at once -- the producer of the many-streams kernels.  `nsinks` sinks of
+ * the same channel layout, each holding one whole file (pushed from a reset decoder, not attached,
+ * not flushed before): their frames are gathered into ONE device batch (every file's first frame
+ * carries the reset flag), synthesised by ONE kernel launch and post-filtered by ONE launch with
+ * one CTA per file and channel pair (the reference runs the loop src/OpusDecoder.cpp:101-119 once
+ * per file).  pcm_out[k] receives decoded samples [skip[k], skip[k] + count[k]) of file k
+ * (interleaved, `channels` wide; the positional pre-skip / end-trim window of opusfile.c:2673-2721);
+ * decoded[k] = samples per channel file k holds in all.  The destinations may be ordinary
+ * (pageable) memory: the samples come back through a ring of pinned buffers and a few host threads.
+ * The sinks are empty and reset afterwards. */
+/* Optional, before the first push of a file that will go through nq_celt_sink_flush_many: a worker
+ * thread moves every complete block of 2048 frames to a device buffer of the sink's own while phase
+ * 1 keeps pushing (and returns the pinned block to the pool), so that flush_many only gathers
+ * device to device instead of uploading whole files after phase 1 has ended.  expected_frames:
+ * how many frames the file is expected to hold (sizes the device buffer; 0 = unknown, it grows). */
+NQ_API int nq_celt_sink_begin_upload(nq_celt_sink *sink, nq_celt_ctx *ctx, int64_t expected_frames);
+NQ_API int nq_celt_sink_flush_many(nq_celt_sink *const *sinks, int nsinks, nq_celt_ctx *ctx, float *const *pcm_out,
+                                   const int64_t *skip, const int64_t *count, int64_t *decoded);
 /* OPUS_RESET_STATE (celt_decoder_clean.c:846-859): the next frame pushed for every
  * stream starts from a cleared decoder (tail, history, memory), wherever that
  * falls relative to the flushes. */

@@ -53,6 +53,7 @@
 
 #include "nq_celt_synth.h"
 #include "nq_phase1_session.h"
+#include "OpusBatchLoader.h"
 
 // ---- phase 1 across the streams of a multistream packet ------------------------------------
 // Internal entry points of the reference's libopus (opus_private.h:109-111, :140-145; compiled
@@ -134,7 +135,15 @@ double now_s()
 
 struct SinkHolder {
     nq_celt_sink *s = nullptr;
-    ~SinkHolder() { nq_celt_sink_destroy(s); }
+    SinkHolder() = default;
+    SinkHolder(const SinkHolder &) = delete;
+    SinkHolder &operator=(const SinkHolder &) = delete;
+    void reset()
+    {
+        nq_celt_sink_destroy(s);
+        s = nullptr;
+    }
+    ~SinkHolder() { reset(); }
 };
 
 // Helper threads that live for one file: the work items of a packet are tiny (tens of
@@ -473,4 +482,156 @@ void nqr::OpusDecoder::LoadFromBuffer(AudioData *data, const std::vector<uint8_t
 std::vector<std::string> nqr::OpusDecoder::GetSupportedFileExtensions()
 {
     return {"opus"};
+}
+
+////////////////////////
+// Many files at once //
+////////////////////////
+
+namespace {
+
+struct BatchFile {
+    std::string path;
+    AudioData *d = nullptr;
+    SinkHolder sink;
+    int64_t preSkip = 0, totalSamples = 0;
+    int gainQ8 = 0;
+    std::string layoutKey;     // files with equal keys share one phase-2 batch
+    bool batched = false;      // false: goes through the ordinary loader
+    long long frames = 0;      // CELT frames (per stream)
+    std::string error;
+};
+
+// Phase 1 of one file into a sink of its own; phase 2 comes later, for all files at once -- only the
+// upload of the coefficients to the device runs along (nq_celt_sink_begin_upload).
+void batch_phase1(BatchFile &bf, nq_celt_ctx *ctx)
+{
+    NyquistFileBuffer file = nqr::ReadFile(bf.path);
+    int err;
+    std::unique_ptr<OggOpusFile, OpusFileCloser> fh(op_test_memory(file.buffer.data(), file.buffer.size(), &err));
+    if (!fh) throw std::runtime_error("File is not a valid ogg vorbis file");
+    if (op_test_open(fh.get()) != 0) {
+        fh.release();
+        throw std::runtime_error("Could not open file");
+    }
+    const OpusHead *header = op_head(fh.get(), 0);
+    AudioData *d = bf.d;
+    d->sampleRate = OPUS_SAMPLE_RATE;
+    d->channelCount = (uint32_t)header->channel_count;
+    d->sourceFormat = MakeFormatForBits(32, true, false);
+    bf.totalSamples = op_pcm_total(fh.get(), -1);
+    d->lengthSeconds = double(uint64_t(bf.totalSamples / OPUS_SAMPLE_RATE));
+    d->frameSize = (uint32_t)header->channel_count * GetFormatBitsPerSample(d->sourceFormat);
+    if (op_link_count(fh.get()) != 1) return;   // not batched: the ordinary loader reports it
+    bf.preSkip = header->pre_skip;
+    bf.gainQ8 = header->output_gain;
+    const int ch = header->channel_count;
+    if (nq_celt_sink_create(&bf.sink.s, ch, header->stream_count, header->coupled_count, header->mapping) != NQ_OK) return;
+    bf.layoutKey = std::to_string(ch) + "/" + std::to_string(header->stream_count) + "/" + std::to_string(header->coupled_count) + "/" +
+                   std::string(reinterpret_cast<const char *>(header->mapping), (size_t)ch);
+    if (nq_celt_sink_begin_upload(bf.sink.s, ctx, (bf.totalSamples + bf.preSkip) / 960 + 8) != NQ_OK)
+        throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(bf.sink.s));
+    std::vector<float> placeholder(size_t(5760) * ch);
+    int64_t framesRead = 0;
+    nq_phase1_begin(bf.sink.s);
+    for (;;) {
+        const int n = op_read_float(fh.get(), placeholder.data(), (int)placeholder.size(), nullptr);
+        if (n <= 0) {
+            if (n < 0) framesRead = -1;
+            break;
+        }
+        framesRead += n;
+    }
+    const nq_phase1_stats st = nq_phase1_end();
+    // the batched phase 2 covers what a CELT-only file needs; SILK layers, mode switches and
+    // anything irregular stay with the ordinary loader
+    bf.batched = framesRead == bf.totalSamples && !st.saw_silk && !st.mode_switch && !st.irregular_celt && !st.error &&
+                 st.frames > 0 && st.streams_seen == header->stream_count;
+    bf.frames = st.frames / header->stream_count;
+    if (bf.batched) d->samples.resize(size_t(bf.totalSamples) * ch);   // (zero-fill on this file's own thread)
+}
+
+}   // namespace
+
+nqr::OpusBatchStats nqr::LoadOpusBatch(const std::vector<std::string> &paths, std::vector<std::shared_ptr<AudioData>> &out, int threads)
+{
+    OpusBatchStats stats;
+    const double t0 = now_s();
+    const int K = (int)paths.size();
+    out.clear();
+    std::vector<BatchFile> files(K);
+    for (int i = 0; i < K; i++) {
+        out.push_back(std::make_shared<AudioData>());
+        files[i].path = paths[i];
+        files[i].d = out[i].get();
+    }
+    ContextLease ctx;
+    // ---- phase 1 of all files, `threads` at a time ----
+    int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > K) nthreads = K;
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++)
+        pool.emplace_back([&] {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= K) return;
+                try {
+                    batch_phase1(files[i], ctx.get());
+                } catch (const std::exception &e) {
+                    files[i].error = e.what();
+                }
+            }
+        });
+    for (std::thread &t : pool) t.join();
+    for (const BatchFile &bf : files)
+        if (!bf.error.empty()) throw std::runtime_error(bf.path + ": " + bf.error);
+    const double t1 = now_s();
+    stats.phase1Seconds = t1 - t0;
+    // ---- phase 2: one batch per channel layout ----
+    const long long launches0 = nq_celt_launch_count(ctx.get());
+    std::vector<char> done(K, 0);
+    for (int i = 0; i < K; i++) {
+        if (done[i] || !files[i].batched) continue;
+        std::vector<int> group;
+        for (int j = i; j < K; j++)
+            if (!done[j] && files[j].batched && files[j].layoutKey == files[i].layoutKey) group.push_back(j);
+        std::vector<nq_celt_sink *> sinks;
+        std::vector<float *> dst;
+        std::vector<int64_t> skip, count, decoded(group.size(), 0);
+        for (int j : group) {
+            sinks.push_back(files[j].sink.s);
+            dst.push_back(files[j].d->samples.data());
+            skip.push_back(files[j].preSkip);
+            count.push_back(files[j].totalSamples);
+            stats.frames += files[j].frames;
+            done[j] = 1;
+        }
+        const int rc = nq_celt_sink_flush_many(sinks.data(), (int)sinks.size(), ctx.get(), dst.data(), skip.data(), count.data(), decoded.data());
+        if (rc != NQ_OK)
+            throw std::runtime_error(std::string("two-phase Opus decoder: batched phase 2 failed: ") + nq_celt_sink_last_error(sinks[0]));
+        for (int j : group) {
+            BatchFile &bf = files[j];
+            int gainQ8 = bf.gainQ8 < -32768 ? -32768 : (bf.gainQ8 > 32767 ? 32767 : bf.gainQ8);
+            if (gainQ8 != 0) {   // opus_decoder_clean.c:578-588
+                const float gain = (float)std::exp(0.6931471805599453094 * (6.48814081e-4f * gainQ8));
+                for (float &v : bf.d->samples) v *= gain;
+            }
+            stats.filesBatched++;
+        }
+    }
+    stats.launches = (int)(nq_celt_launch_count(ctx.get()) - launches0);
+    const double t2 = now_s();
+    stats.phase2Seconds = t2 - t1;
+    // ---- the files the batch does not cover: the ordinary two-phase loader, one by one ----
+    for (int i = 0; i < K; i++) {
+        if (files[i].batched) continue;
+        files[i].sink.reset();
+        *files[i].d = AudioData();
+        nqr::OpusDecoder().LoadFromPath(files[i].d, files[i].path);
+        stats.filesSingle++;
+    }
+    stats.totalSeconds = now_s() - t0;
+    return stats;
 }

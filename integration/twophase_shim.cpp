@@ -3,6 +3,7 @@
 // in place (the AudioData lives until nq_twophase_free): copying 86 MB out of the vector would be a
 // cost of this wrapper, not of Load.
 #include "Decoders.h"
+#include "OpusBatchLoader.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -10,6 +11,8 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace {
 std::mutex g_mu;
@@ -39,6 +42,34 @@ __attribute__((visibility("default"))) int nq_twophase_load(const char *path, fl
         return 0;
     } catch (const std::exception &e) {
         std::cerr << "nq_twophase_load: " << e.what() << std::endl;
+        return -1;
+    }
+}
+
+// nqr::LoadOpusBatch: n paths -> samples[i] / counts[i] / channels[i] (each freed with nq_twophase_free).
+// stats: phase 1 s, phase 2 s, total s, files batched, files single, CELT frames, kernel launches.
+__attribute__((visibility("default"))) int nq_twophase_load_batch(const char *const *paths, int n, int threads, float **samples,
+                                                                   size_t *counts, int *channels, double stats[7])
+{
+    try {
+        std::vector<std::string> p(paths, paths + n);
+        std::vector<std::shared_ptr<nqr::AudioData>> out;
+        const nqr::OpusBatchStats st = nqr::LoadOpusBatch(p, out, threads);
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (int i = 0; i < n; i++) {
+            std::unique_ptr<nqr::AudioData> d(new nqr::AudioData(std::move(*out[i])));
+            counts[i] = d->samples.size();
+            channels[i] = d->channelCount;
+            samples[i] = d->samples.data();
+            g_live[d->samples.data()] = std::move(d);
+        }
+        if (stats) {
+            stats[0] = st.phase1Seconds; stats[1] = st.phase2Seconds; stats[2] = st.totalSeconds;
+            stats[3] = st.filesBatched; stats[4] = st.filesSingle; stats[5] = (double)st.frames; stats[6] = st.launches;
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        std::cerr << "nq_twophase_load_batch: " << e.what() << std::endl;
         return -1;
     }
 }

@@ -31,6 +31,11 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+
 #include "../../include/nq_celt_synth.h"
 
 namespace {
@@ -137,6 +142,29 @@ struct Job {
     long long nframes = 0;
 };
 
+// Device memory of the many-files path: stream-ordered allocations from the device's default pool,
+// which is told to keep what is freed (cudaMalloc / cudaFree of gigabytes per call cost tens of
+// milliseconds and synchronise the device).
+void keep_pool_memory(int device)
+{
+    static std::mutex mu;
+    static std::vector<char> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)done.size() <= device) done.resize(device + 1, 0);
+    if (done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[device] = 1;
+}
+
+double wall_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 }  // namespace
 
 struct nq_celt_sink {
@@ -165,6 +193,17 @@ struct nq_celt_sink {
     std::deque<Job> queue;
     bool stop = false, busy = false;
     int worker_rc = NQ_OK;
+    // upload mode (nq_celt_sink_begin_upload, the many-files loader): the worker only moves every
+    // complete block to a device buffer of the sink's own while phase 1 goes on, and phase 2 comes
+    // later, for many sinks at once (nq_celt_sink_flush_many)
+    bool upload = false;
+    cudaStream_t up_stream = nullptr;
+    float *d_coef = nullptr;         // [up_cap][D][960]
+    uint8_t *d_flags = nullptr;      // [up_cap][streams]
+    long long up_cap = 0, up_frames = 0, up_expect = 0;
+    int up_device = 0;
+    std::vector<nq_celt_post_frame> up_post;   // side info and flags of the uploaded frames stay on the host
+    std::vector<uint8_t> up_flags;
 };
 
 namespace {
@@ -212,6 +251,42 @@ int decode_block(nq_celt_sink *s, nq_celt_ctx *ctx, const Block &b, long long nf
     return NQ_OK;
 }
 
+// Upload mode: frames [up_frames, up_frames + nframes) of the sink -> its device buffer (grown
+// geometrically; the copy returns before the block goes back to the pool).
+int upload_block(nq_celt_sink *s, const Block &b, long long nframes)
+{
+    if (cudaSetDevice(nq_celt_ctx_device(s->ctx)) != cudaSuccess) return sink_fail(s, NQ_INTERNAL_ERROR, "cudaSetDevice");
+    const size_t row = sizeof(float) * (size_t)s->D * kFrame;
+    if (s->up_frames + nframes > s->up_cap) {
+        long long cap = s->up_cap > 0 ? 2 * s->up_cap : (s->up_expect > 0 ? s->up_expect : 4 * kBlockFrames);
+        while (cap < s->up_frames + nframes) cap *= 2;
+        float *nc = nullptr;
+        uint8_t *nf = nullptr;
+        if (cudaMallocAsync(&nc, row * cap, s->up_stream) != cudaSuccess || cudaMallocAsync(&nf, (size_t)cap * s->streams, s->up_stream) != cudaSuccess) {
+            if (nc) cudaFreeAsync(nc, s->up_stream);
+            return sink_fail(s, NQ_ALLOC_FAIL, "device memory for the uploaded frames");
+        }
+        if (s->up_frames > 0) {
+            cudaMemcpyAsync(nc, s->d_coef, row * s->up_frames, cudaMemcpyDeviceToDevice, s->up_stream);
+            cudaMemcpyAsync(nf, s->d_flags, (size_t)s->up_frames * s->streams, cudaMemcpyDeviceToDevice, s->up_stream);
+            cudaStreamSynchronize(s->up_stream);
+        }
+        if (s->d_coef) cudaFreeAsync(s->d_coef, s->up_stream);
+        if (s->d_flags) cudaFreeAsync(s->d_flags, s->up_stream);
+        s->d_coef = nc;
+        s->d_flags = nf;
+        s->up_cap = cap;
+    }
+    if (cudaMemcpyAsync(s->d_coef + (size_t)s->up_frames * s->D * kFrame, b.coef, row * nframes, cudaMemcpyHostToDevice, s->up_stream) != cudaSuccess ||
+        cudaMemcpyAsync(s->d_flags + (size_t)s->up_frames * s->streams, b.flags, (size_t)nframes * s->streams, cudaMemcpyHostToDevice, s->up_stream) != cudaSuccess)
+        return sink_fail(s, NQ_INTERNAL_ERROR, "host to device copy of a block");
+    s->up_post.insert(s->up_post.end(), b.post, b.post + (size_t)nframes * s->streams);
+    s->up_flags.insert(s->up_flags.end(), b.flags, b.flags + (size_t)nframes * s->streams);
+    if (cudaStreamSynchronize(s->up_stream) != cudaSuccess) return sink_fail(s, NQ_INTERNAL_ERROR, "host to device copy of a block");
+    s->up_frames += nframes;
+    return NQ_OK;
+}
+
 void worker_main(nq_celt_sink *s)
 {
     for (;;) {
@@ -225,7 +300,9 @@ void worker_main(nq_celt_sink *s)
             s->busy = true;
         }
         int rc = s->worker_rc;
-        if (rc == NQ_OK) {
+        if (rc == NQ_OK && s->upload) {
+            rc = upload_block(s, job.block, job.nframes);
+        } else if (rc == NQ_OK) {
             const long long n = block_samples(s, job.block, job.nframes);
             const size_t need = sizeof(float) * (size_t)n * s->channels;
             if (need > s->out_bytes) {
@@ -323,6 +400,15 @@ void nq_celt_sink_destroy(nq_celt_sink *s)
     for (Job &j : s->queue) recycle_block(j.block);
     for (Block &b : s->blocks) recycle_block(b);
     recycle_out(s->out, s->out_bytes);
+    if (s->d_coef || s->d_flags || s->up_stream) {
+        cudaSetDevice(s->up_device);
+        if (s->up_stream) {
+            if (s->d_coef) cudaFreeAsync(s->d_coef, s->up_stream);
+            if (s->d_flags) cudaFreeAsync(s->d_flags, s->up_stream);
+            cudaStreamSynchronize(s->up_stream);
+            cudaStreamDestroy(s->up_stream);
+        }
+    }
     delete s;
 }
 
@@ -466,6 +552,320 @@ int nq_celt_sink_flush_pinned(nq_celt_sink *s, nq_celt_ctx *ctx, const float **p
     }
     const int rc = nq_celt_sink_flush(s, ctx, s->out, (int64_t)(s->out_bytes / sizeof(float) / s->channels), nsamples);
     if (rc == NQ_OK) *pcm = s->out;
+    return rc;
+}
+
+int nq_celt_sink_begin_upload(nq_celt_sink *s, nq_celt_ctx *ctx, int64_t expected_frames)
+{
+    if (!s || !ctx) return NQ_BAD_ARG;
+    if (s->ctx) return sink_fail(s, NQ_INVALID_STATE, "sink already attached");
+    if (min_pushed(s) != 0 || s->have_state) return sink_fail(s, NQ_INVALID_STATE, "begin_upload: before the first push of a whole file");
+    s->up_device = nq_celt_ctx_device(ctx);
+    if (cudaSetDevice(s->up_device) != cudaSuccess) return sink_fail(s, NQ_INTERNAL_ERROR, "cudaSetDevice");
+    if (!s->up_stream && cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return sink_fail(s, NQ_INTERNAL_ERROR, "cudaStreamCreate");
+    keep_pool_memory(s->up_device);
+    s->ctx = ctx;
+    s->upload = true;
+    s->up_expect = expected_frames > 0 ? expected_frames : 0;
+    s->up_frames = 0;
+    s->up_post.clear();
+    s->up_flags.clear();
+    s->dst = nullptr;
+    s->first_block = 0;
+    s->stop = false;
+    s->worker_rc = NQ_OK;
+    s->worker = std::thread(worker_main, s);
+    return NQ_OK;
+}
+
+namespace {
+
+// Upload mode, end of phase 1: the last partial block goes up, the worker stops.
+int finish_upload(nq_celt_sink *s)
+{
+    const long long n = min_pushed(s);
+    int rc = NQ_OK;
+    for (long long v : s->pushed)
+        if (v != n) rc = sink_fail(s, NQ_INVALID_STATE, "streams have pushed different numbers of frames");
+    const long long rest = n - s->first_block * kBlockFrames;
+    if (rc == NQ_OK && rest > 0) {
+        Job job;
+        job.block = s->blocks.front();
+        job.nframes = rest;
+        s->blocks.pop_front();
+        s->first_block++;
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->queue.push_back(job);
+        }
+        s->cv.notify_all();
+    }
+    {
+        std::unique_lock<std::mutex> lk(s->mu);
+        s->cv.wait(lk, [&] { return s->queue.empty() && !s->busy; });
+        if (rc == NQ_OK) rc = s->worker_rc;
+    }
+    stop_worker(s);
+    s->ctx = nullptr;
+    if (rc == NQ_OK && s->up_frames != n) rc = sink_fail(s, NQ_INTERNAL_ERROR, "upload lost frames");
+    return rc;
+}
+
+}  // namespace
+
+int nq_celt_sink_flush_many(nq_celt_sink *const *sinks, int nsinks, nq_celt_ctx *ctx, float *const *pcm_out,
+                            const int64_t *skip, const int64_t *count, int64_t *decoded)
+{
+    if (!sinks || nsinks < 1 || !ctx || !pcm_out || !skip || !count) return NQ_BAD_ARG;
+    nq_celt_sink *s0 = sinks[0];
+    if (!s0) return NQ_BAD_ARG;
+    int rc = NQ_OK;
+    // ---- what the batch holds ----
+    std::vector<long long> nfr(nsinks), first_frame(nsinks + 1, 0), first_sample(nsinks + 1, 0);
+    bool any_short = false;
+    for (int k = 0; k < nsinks; k++) {
+        nq_celt_sink *s = sinks[k];
+        if (!s) return NQ_BAD_ARG;
+        if (s->channels != s0->channels || s->streams != s0->streams || s->coupled != s0->coupled ||
+            memcmp(s->mapping, s0->mapping, s0->channels) != 0)
+            return sink_fail(s0, NQ_BAD_ARG, "flush_many: the sinks of one call must share the channel layout");
+        if (s->upload) {
+            if (s->ctx && finish_upload(s) != NQ_OK) {
+                snprintf(s0->err, sizeof s0->err, "flush_many: %s", s->err);
+                rc = NQ_INTERNAL_ERROR;
+            }
+        } else if (s->ctx) {
+            return sink_fail(s0, NQ_INVALID_STATE, "flush_many: a sink is in streaming mode");
+        }
+        if (s->have_state) return sink_fail(s0, NQ_INVALID_STATE, "flush_many: a sink carries state from an earlier flush (whole files only)");
+    }
+    for (int k = 0; k < nsinks && rc == NQ_OK; k++) {
+        nq_celt_sink *s = sinks[k];
+        const long long n = s->upload ? s->up_frames : min_pushed(s);
+        if (!s->upload)
+            for (long long v : s->pushed)
+                if (v != n) return sink_fail(s0, NQ_INVALID_STATE, "flush_many: streams have pushed different numbers of frames");
+        nfr[k] = n;
+        first_frame[k + 1] = first_frame[k] + n;
+        long long samples = 0;
+        auto scan = [&](const nq_celt_post_frame *post, const uint8_t *flags, long long m, bool head) -> int {
+            for (long long f = 0; f < m; f++) {
+                const int N = post[f * s->streams].N;
+                any_short = any_short || N != kFrame;
+                for (int st = 1; st < s->streams; st++)
+                    if (post[f * s->streams + st].N != N)
+                        return sink_fail(s0, NQ_BAD_ARG, "streams of one multistream packet must share the frame size");
+                for (int st = 0; st < s->streams; st++)
+                    if ((f > 0 || !head) && (flags[f * s->streams + st] & 8) && s->streams > 1)
+                        return sink_fail(s0, NQ_UNIMPLEMENTED, "flush_many: decoder resets inside a multistream file");
+                samples += N;
+            }
+            return NQ_OK;
+        };
+        if (s->upload) {
+            rc = scan(s->up_post.data(), s->up_flags.data(), n, true);
+        } else {
+            long long done = 0;
+            for (size_t b = 0; done < n && rc == NQ_OK; b++) {
+                const long long m = n - done < kBlockFrames ? n - done : kBlockFrames;
+                rc = scan(s->blocks[b].post, s->blocks[b].flags, m, b == 0);
+                done += m;
+            }
+        }
+        first_sample[k + 1] = first_sample[k] + samples;
+        if (decoded) decoded[k] = samples;
+        if (rc == NQ_OK && (skip[k] < 0 || count[k] < 0 || skip[k] + count[k] > samples || (count[k] > 0 && !pcm_out[k])))
+            rc = sink_fail(s0, NQ_BAD_ARG, "flush_many: output window outside the decoded samples");
+    }
+    const long long T = first_frame[nsinks], S = first_sample[nsinks];
+    const int D = s0->D, C = s0->channels, ST = s0->streams;
+    float *d_coef = nullptr, *d_pcm = nullptr;
+    uint8_t *d_flags = nullptr;
+    long long *d_offs = nullptr;
+    std::vector<nq_celt_post_frame> post;
+    std::vector<int64_t> seg, offs;
+    std::vector<uint8_t> head(ST);
+    cudaStream_t st = (cudaStream_t)nq_celt_ctx_stream(ctx);
+    const int device = nq_celt_ctx_device(ctx);
+    const bool timing = getenv("NQ_SINK_TIMING") != nullptr;
+    const double tm0 = wall_s();
+    double tm_gather = 0, tm_kernels = 0;
+    if (rc == NQ_OK && T > 0) {
+        post.resize((size_t)T * ST);
+        if (cudaSetDevice(device) != cudaSuccess) rc = sink_fail(s0, NQ_INTERNAL_ERROR, "cudaSetDevice");
+        keep_pool_memory(device);
+        if (rc == NQ_OK &&
+            (cudaMallocAsync(&d_coef, sizeof(float) * (size_t)T * D * kFrame, st) != cudaSuccess ||
+             cudaMallocAsync(&d_pcm, sizeof(float) * (size_t)S * C + 16, st) != cudaSuccess || cudaMallocAsync(&d_flags, (size_t)T * ST, st) != cudaSuccess ||
+             (any_short && cudaMallocAsync(&d_offs, sizeof(long long) * (size_t)(T + 1), st) != cudaSuccess)))
+            rc = sink_fail(s0, NQ_ALLOC_FAIL, "flush_many: device memory for the batch");
+        // ---- gather: device to device from the sinks that uploaded their blocks during phase 1,
+        // host to device from the pinned blocks of the others; every file (and every reset inside a
+        // file) opens a segment of the post stage ----
+        if (any_short) offs.reserve(T + 1);
+        long long pos = 0;
+        auto note = [&](const nq_celt_post_frame *p, const uint8_t *fl, long long f0, long long m, bool first_of_file) {
+            for (long long f = 0; f < m; f++) {
+                if ((fl[f * ST] & 8) || (first_of_file && f == 0)) seg.push_back(f0 + f);
+                if (any_short) offs.push_back(pos);
+                pos += p[f * ST].N;
+            }
+            memcpy(post.data() + (size_t)f0 * ST, p, sizeof(nq_celt_post_frame) * (size_t)m * ST);
+        };
+        bool copy_failed = false;
+        for (int k = 0; k < nsinks && rc == NQ_OK; k++) {
+            nq_celt_sink *s = sinks[k];
+            if (nfr[k] == 0) continue;
+            const long long f0 = first_frame[k];
+            if (s->upload) {
+                note(s->up_post.data(), s->up_flags.data(), f0, nfr[k], true);
+                copy_failed |= cudaMemcpyAsync(d_coef + (size_t)f0 * D * kFrame, s->d_coef, sizeof(float) * (size_t)nfr[k] * D * kFrame, cudaMemcpyDeviceToDevice, st) != cudaSuccess;
+                copy_failed |= cudaMemcpyAsync(d_flags + (size_t)f0 * ST, s->d_flags, (size_t)nfr[k] * ST, cudaMemcpyDeviceToDevice, st) != cudaSuccess;
+            } else {
+                long long done = 0;
+                for (size_t b = 0; done < nfr[k]; b++) {
+                    const long long m = nfr[k] - done < kBlockFrames ? nfr[k] - done : kBlockFrames;
+                    const Block &blk = s->blocks[b];
+                    note(blk.post, blk.flags, f0 + done, m, b == 0);
+                    copy_failed |= cudaMemcpyAsync(d_coef + (size_t)(f0 + done) * D * kFrame, blk.coef, sizeof(float) * (size_t)m * D * kFrame, cudaMemcpyHostToDevice, st) != cudaSuccess;
+                    copy_failed |= cudaMemcpyAsync(d_flags + (size_t)(f0 + done) * ST, blk.flags, (size_t)m * ST, cudaMemcpyHostToDevice, st) != cudaSuccess;
+                    done += m;
+                }
+            }
+            // the file starts from a reset decoder: flag bit 3 on its first frame, every stream
+            const uint8_t *fl0 = s->upload ? s->up_flags.data() : s->blocks[0].flags;
+            for (int x = 0; x < ST; x++) head[x] = fl0[x] | 8;
+            copy_failed |= cudaMemcpyAsync(d_flags + (size_t)f0 * ST, head.data(), ST, cudaMemcpyHostToDevice, st) != cudaSuccess;
+            copy_failed |= cudaStreamSynchronize(st) != cudaSuccess;   // (`head` is reused; the blocks are pinned, the copies short)
+        }
+        if (copy_failed && rc == NQ_OK) rc = sink_fail(s0, NQ_INTERNAL_ERROR, "flush_many: gathering the batch on the device");
+        tm_gather = wall_s();
+        seg.push_back(T);
+        if (rc == NQ_OK && any_short) {
+            offs.push_back(pos);
+            if (cudaMemcpyAsync(d_offs, offs.data(), sizeof(long long) * offs.size(), cudaMemcpyHostToDevice, st) != cudaSuccess)
+                rc = sink_fail(s0, NQ_INTERNAL_ERROR, "flush_many: host to device copy");
+        }
+        // ---- ONE synthesis launch, ONE post launch ----
+        if (rc == NQ_OK) {
+            rc = nq_celt_synth_batch_device_ms(ctx, d_coef, d_flags, nullptr, nullptr, nullptr, d_pcm, nullptr,
+                                               any_short ? reinterpret_cast<const int64_t *>(d_offs) : nullptr, T, C, ST, s0->coupled,
+                                               s0->mapping, st);
+            if (rc == NQ_OK)
+                rc = nq_celt_post_segments_device(ctx, d_pcm, post.data(), seg.data(), (int)seg.size() - 1, T, C, ST, s0->coupled,
+                                                  s0->mapping, st);
+            if (rc != NQ_OK) snprintf(s0->err, sizeof s0->err, "flush_many: phase 2 failed: %s", nq_celt_last_error(ctx));
+        }
+        // ---- PCM back.  The destinations are ordinary (pageable) memory, where a plain copy is paced by
+        // the driver's host-side staging on one thread; so the samples come back in 16 MB pieces through a
+        // ring of pinned buffers at the PCIe rate, and a few host threads move the pieces on to their
+        // destinations while the next ones are in flight. ----
+        if (rc == NQ_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = sink_fail(s0, NQ_INTERNAL_ERROR, "flush_many: CUDA error");
+        tm_kernels = wall_s();
+        if (rc == NQ_OK) {
+            struct Piece { int k; size_t off, n; };   // floats [off, off + n) of file k's window
+            std::vector<Piece> pieces;
+            const size_t piece_floats = (size_t(16) << 20) / sizeof(float);
+            for (int k = 0; k < nsinks; k++)
+                for (size_t o = 0, n = (size_t)count[k] * C; o < n; o += piece_floats)
+                    pieces.push_back({k, o, n - o < piece_floats ? n - o : piece_floats});
+            constexpr int kRing = 12;
+            const int nth = 6;
+            float *ring[kRing] = {};
+            size_t ring_bytes[kRing] = {};
+            cudaEvent_t ev[kRing] = {};
+            bool ok = true;
+            for (int r = 0; r < kRing && ok; r++) {
+                ring[r] = take_out(piece_floats * sizeof(float), &ring_bytes[r]);
+                ok = ring[r] != nullptr && cudaEventCreateWithFlags(&ev[r], cudaEventDisableTiming) == cudaSuccess;
+            }
+            if (!ok) rc = sink_fail(s0, NQ_ALLOC_FAIL, "flush_many: pinned staging");
+            // piece i uses slot i % kRing; issued[i] / copied[i] hand the slots back and forth
+            std::mutex mu;
+            std::condition_variable cv;
+            size_t issued = 0, next_copy = 0;
+            std::vector<char> copied(pieces.size(), 0);
+            bool failed = false;
+            std::vector<std::thread> th;
+            if (rc == NQ_OK)
+                for (int t = 0; t < nth; t++)
+                    th.emplace_back([&] {
+                        cudaSetDevice(device);
+                        for (;;) {
+                            size_t i;
+                            {
+                                std::unique_lock<std::mutex> lk(mu);
+                                cv.wait(lk, [&] { return failed || next_copy >= pieces.size() || next_copy < issued; });
+                                if (failed || next_copy >= pieces.size()) return;
+                                i = next_copy++;
+                            }
+                            const Piece &pc = pieces[i];
+                            const bool good = cudaEventSynchronize(ev[i % kRing]) == cudaSuccess;
+                            if (good) memcpy(pcm_out[pc.k] + pc.off, ring[i % kRing], pc.n * sizeof(float));
+                            {
+                                std::lock_guard<std::mutex> lk(mu);
+                                copied[i] = 1;
+                                if (!good) failed = true;
+                            }
+                            cv.notify_all();
+                        }
+                    });
+            for (size_t i = 0; i < pieces.size() && rc == NQ_OK; i++) {
+                if (i >= kRing) {   // the slot's previous piece must have left it
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return failed || copied[i - kRing]; });
+                    if (failed) break;
+                }
+                const Piece &pc = pieces[i];
+                const bool good = cudaMemcpyAsync(ring[i % kRing], d_pcm + (size_t)(first_sample[pc.k] + skip[pc.k]) * C + pc.off, pc.n * sizeof(float),
+                                                  cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                                  cudaEventRecord(ev[i % kRing], st) == cudaSuccess;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (good) issued = i + 1;
+                    else failed = true;
+                }
+                cv.notify_all();
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (issued < pieces.size()) failed = true;   // (nothing more will be issued: let the threads go)
+            }
+            cv.notify_all();
+            for (std::thread &x : th) x.join();
+            cudaStreamSynchronize(st);
+            if (failed && rc == NQ_OK && !pieces.empty()) {
+                bool all = true;
+                for (char c : copied) all = all && c;
+                if (!all) rc = sink_fail(s0, NQ_INTERNAL_ERROR, "flush_many: device to host copy");
+            }
+            for (int r = 0; r < kRing; r++) {
+                if (ev[r]) cudaEventDestroy(ev[r]);
+                recycle_out(ring[r], ring_bytes[r]);
+            }
+        }
+    }
+    if (d_coef) cudaFreeAsync(d_coef, st);
+    if (d_pcm) cudaFreeAsync(d_pcm, st);
+    if (d_flags) cudaFreeAsync(d_flags, st);
+    if (d_offs) cudaFreeAsync(d_offs, st);
+    if (timing)
+        fprintf(stderr, "nq_celt_sink_flush_many: %d files, %lld frames: scan+alloc+gather %.1f ms, kernels %.1f ms, copy back %.1f ms\n",
+                nsinks, T, (tm_gather - tm0) * 1e3, (tm_kernels - tm_gather) * 1e3, (wall_s() - tm_kernels) * 1e3);
+    for (int k = 0; k < nsinks; k++) {   // empty and reset, whatever happened
+        nq_celt_sink *s = sinks[k];
+        std::fill(s->pushed.begin(), s->pushed.end(), 0);
+        std::fill(s->reset_next.begin(), s->reset_next.end(), 0);
+        s->have_state = false;
+        s->first_block = 0;
+        if (s->upload) {
+            s->upload = false;
+            s->up_frames = 0;
+            s->up_post.clear();
+            s->up_flags.clear();
+        }
+    }
     return rc;
 }
 

@@ -400,6 +400,10 @@ const char *nq_celt_last_error(const nq_celt_ctx *ctx) { return ctx ? ctx->err :
 
 long long nq_celt_launch_count(const nq_celt_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int nq_celt_ctx_device(const nq_celt_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+void *nq_celt_ctx_stream(const nq_celt_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
 int nq_celt_device_count(void)
 {
     int n = 0;

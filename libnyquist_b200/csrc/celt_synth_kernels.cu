@@ -155,10 +155,6 @@ __device__ __forceinline__ int park_index(int c, int n)
 #ifndef NQ_PART
 #define NQ_PART 0
 #endif
-#ifndef NQ_SHORT_UNROLL
-#define NQ_SHORT_UNROLL 5
-#endif
-constexpr int kShortUnroll = NQ_SHORT_UNROLL;   // k1 iterations per trip of short_stage2's loop
 
 #if NQ_PART == 0
 size_t fast_kernel_smem_bytes() { return sizeof(FastTables) + kWarpsPerCta * sizeof(WarpSmem); }

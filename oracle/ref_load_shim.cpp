@@ -11,6 +11,11 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
 
 namespace {
 std::mutex g_mu;
@@ -37,6 +42,35 @@ __attribute__((visibility("default"))) int nqref_load(const char *path, float **
         std::cerr << "nqref_load: " << e.what() << std::endl;
         return -1;
     }
+}
+
+// K loads of the unmodified reference at the same time, one thread each (`threads` at a time): what a
+// program that needs K files does with the reference on the same cores.  Returns the wall seconds,
+// or a negative number if a Load threw.  The samples are dropped.
+__attribute__((visibility("default"))) double nqref_load_many(const char *const *paths, int n, int threads)
+{
+    std::atomic<int> next{0}, failed{0};
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    if (threads < 1) threads = 1;
+    if (threads > n) threads = n;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&] {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n) return;
+                try {
+                    nqr::NyquistIO loader;
+                    nqr::AudioData data;
+                    loader.Load(&data, std::string(paths[i]));
+                } catch (const std::exception &) {
+                    failed.fetch_add(1);
+                }
+            }
+        });
+    for (std::thread &t : pool) t.join();
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return failed.load() ? -1.0 : dt;
 }
 
 __attribute__((visibility("default"))) void nqref_free(float *p)

@@ -242,3 +242,48 @@ def test_two_phase_load_errors_like_the_reference(twophase, tmp_path):
     assert got is None
     got, *_ = load(twophase, str(tmp_path / "missing.opus"))
     assert got is None
+
+
+def load_batch(L, paths, threads=0):
+    L.nq_twophase_load_batch.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
+                                         C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    n = len(paths)
+    arr = (C.c_char_p * n)(*[p.encode() for p in paths])
+    ptrs = (C.POINTER(C.c_float) * n)()
+    counts, chans, stats = (C.c_size_t * n)(), (C.c_int * n)(), (C.c_double * 7)()
+    t0 = time.perf_counter()
+    rc = L.nq_twophase_load_batch(arr, n, threads, ptrs, counts, chans, stats)
+    wall = time.perf_counter() - t0
+    assert rc == 0
+    out = []
+    for i in range(n):
+        a = np.ctypeslib.as_array(ptrs[i], shape=(counts[i],)).copy().reshape(-1, chans[i])
+        L.nq_twophase_free(ptrs[i])
+        out.append(a)
+    names = ("phase1_s", "phase2_s", "total_s", "files_batched", "files_single", "frames", "launches")
+    return out, dict(zip(names, list(stats))), wall
+
+
+def test_batched_loader_many_files_one_phase2(twophase):
+    """nqr::LoadOpusBatch: K files -> phase 1 on K host threads, ONE synthesis launch + ONE post
+    launch per channel layout (every file a segment that starts from a reset decoder); the files the
+    batch does not cover (hybrid, SILK-only) go through the ordinary loader.  Every file must come
+    out exactly as nqr::NyquistIO::Load gives it one by one."""
+    from conftest import GOLDEN
+    td = os.path.join(os.path.dirname(ref.LIB_PATH), "test_data")
+    paths = [os.path.join(td, f) for f in ("sb-reverie.opus", "short.opus", "sb-reverie-60ms-frames.opus", "short.opus")]
+    paths += [os.path.join(GOLDEN, f) for f in ("surround8.opus", "hybrid.opus", "surround8.opus")]
+    paths = [p for p in paths if os.path.exists(p)]
+    if len(paths) < 3:
+        pytest.skip("test files not staged")
+    singles = [load(twophase, p)[0] for p in paths]
+    got, st, wall = load_batch(twophase, paths)
+    nhyb = sum(p.endswith("hybrid.opus") for p in paths)
+    assert st["files_single"] == nhyb and st["files_batched"] == len(paths) - nhyb
+    layouts = len({s.shape[1] for s, p in zip(singles, paths) if not p.endswith("hybrid.opus")})
+    assert st["launches"] == 2 * layouts, st          # one synthesis + one post launch per channel layout
+    for p, a, b in zip(paths, got, singles):
+        assert a.shape == b.shape, p
+        assert np.array_equal(a, b), (p, float(np.abs(a - b).max()))
+    print(f"\nbatched loader: {len(paths)} files in {wall * 1e3:.0f} ms (phase 1 {st['phase1_s'] * 1e3:.0f} ms on host threads, "
+          f"phase 2 {st['phase2_s'] * 1e3:.0f} ms, {int(st['frames'])} frames, {int(st['launches'])} launches)")
