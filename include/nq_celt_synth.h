@@ -231,6 +231,19 @@ NQ_API const char *nq_celt_sink_last_error(const nq_celt_sink *sink);
  * (:273-284), post = the comb_filter arguments of the frame (:660-669). */
 NQ_API int nq_celt_sink_push(nq_celt_sink *sink, int stream, const float *freq, int CC, int N, int shortBlocks,
                              const nq_celt_post_frame *post);
+/* Same, for a frame that does not simply follow the one before it in the output (files that switch
+ * between the SILK, hybrid and CELT coding modes, opus_decoder_clean.c:478-487, :499-513, :530-555:
+ * the CELT decoder is not called for every stretch of the output, and the 5 ms redundancy frames are
+ * decoded into a side buffer and cross-faded in by the caller).  Streaming mode, single-stream files.
+ *   dest >= 0   first output sample (per channel, before the pre-skip window) of this frame;
+ *   dest == -1  right after the previous frame (what nq_celt_sink_push does);
+ *   dest <= -2  a side frame with the caller's tag -2 - dest: decoded in sequence like any frame -- it
+ *               takes part in the overlap-add, the post-filter and the de-emphasis state -- but its PCM is
+ *               kept aside: nq_celt_sink_side_get after nq_celt_sink_finish, in push order. */
+NQ_API int nq_celt_sink_push_at(nq_celt_sink *sink, int stream, const float *freq, int CC, int N, int shortBlocks,
+                                const nq_celt_post_frame *post, int64_t dest);
+NQ_API int nq_celt_sink_side_count(const nq_celt_sink *sink);
+NQ_API int nq_celt_sink_side_get(const nq_celt_sink *sink, int i, int64_t *tag, int *nsamples, const float **pcm);
 NQ_API int64_t nq_celt_sink_pending_frames(const nq_celt_sink *sink);
 NQ_API int64_t nq_celt_sink_pending_samples(const nq_celt_sink *sink);   /* per channel */
 /* Phase 2 for everything pushed since the last flush (every stream must have

@@ -373,10 +373,14 @@ private:
             haveOut = true;
         };
         std::vector<float> placeholder(size_t(5760) * ch);   // 120 ms, the largest Opus packet
-        std::vector<float> cpuPcm;   // phase-1 PCM while no CELT frame has turned up: the output of a SILK-only file
+        // phase-1 PCM from sample cpuStart on, kept while no CELT frame has turned up (a SILK-only file:
+        // this IS the output) and from the first SILK layer on (hybrid files, files that switch modes:
+        // the SILK share of the output, fades included)
+        std::vector<float> cpuPcm;
+        int64_t cpuStart = 0;
         int64_t framesRead = 0;
         bool readError = false;
-        nq_phase1_begin(sink.s);
+        nq_phase1_begin(sink.s, header->stream_count);
         ParallelPhase1 pp;
         const int nthreads = phase1_threads(header->stream_count);
         if (nthreads > 1) {
@@ -398,9 +402,13 @@ private:
                 readError = true;
                 break;
             }
+            if (nq_phase1_frames_so_far() == 0 || nq_phase1_saw_silk_so_far()) {
+                if (cpuPcm.empty()) cpuStart = framesRead;
+                cpuPcm.insert(cpuPcm.end(), placeholder.begin(), placeholder.begin() + size_t(n) * ch);
+            } else if (!cpuPcm.empty()) {
+                std::vector<float>().swap(cpuPcm);   // a CELT-only file after all: its placeholder PCM is silence
+            }
             framesRead += n;
-            if (nq_phase1_frames_so_far() == 0 || nq_phase1_saw_silk_so_far()) cpuPcm.insert(cpuPcm.end(), placeholder.begin(), placeholder.begin() + size_t(n) * ch);
-            else if (!cpuPcm.empty()) std::vector<float>().swap(cpuPcm);
         }
         op_set_decode_callback(fileHandle.get(), nullptr, nullptr);
         pp.pool.reset();   // helpers joined before the session goes away
@@ -425,17 +433,65 @@ private:
             g_last_timing[2] = 0;
             return totalSamples > 0;
         }
-        if (st.saw_silk && (st.mode_switch || st.irregular_celt))
-            throw std::runtime_error("two-phase Opus decoder: files that switch between the SILK, hybrid and CELT coding modes (or conceal lost packets) are not supported");
+        if (st.irregular_celt)
+            throw std::runtime_error("two-phase Opus decoder: lost packets and mode switches without redundancy frames need loss concealment, which the bundled decoder does not define");
+        if (st.saw_silk && st.mode_switch && header->stream_count != 1)
+            throw std::runtime_error("two-phase Opus decoder: multistream files that switch between the SILK, hybrid and CELT coding modes are not supported");
         if (st.error) throw std::runtime_error(std::string("two-phase Opus decoder: ") + nq_celt_sink_last_error(sink.s));
         if (st.frames && st.streams_seen != header->stream_count)
             throw std::runtime_error("two-phase Opus decoder: stream count mismatch");
         if (rc != NQ_OK)
             throw std::runtime_error(std::string("two-phase Opus decoder: phase 2 failed: ") + nq_celt_sink_last_error(sink.s));
-        if (framesRead != totalSamples || decoded < preSkip + totalSamples)
+        // CELT-only: phase 2 produced every sample; with a SILK layer the CELT decoder skips stretches
+        // of the output, and the packet frames' own accounting must cover the file
+        if (framesRead != totalSamples || (st.saw_silk ? st.samples : decoded) < preSkip + totalSamples)
             throw std::runtime_error("two-phase Opus decoder: sample accounting does not match opusfile's");
 
-        // ---- positional post-processing of the layers above the CELT decoder ----
+        // ---- what the layers above the CELT decoder do to its output; everything here is linear in it ----
+        // the fades of a mode switch, opus_decoder_clean.c:530-575 (window = the CELT mode's, squared)
+        if (!st.fixups.empty()) {
+            float window[120];
+            nq_celt_debug_tables(nullptr, nullptr, window, nullptr);
+            auto at = [&](int64_t p) -> float * {   // sample p of the output timeline, or null outside the file's window
+                const int64_t i = p - preSkip;
+                return (i >= 0 && i < totalSamples) ? out + size_t(i) * ch : nullptr;
+            };
+            for (const nq_phase1_fixup &f : st.fixups) {
+                const float *side = nullptr;
+                if (f.side >= 0) {
+                    int64_t tag = -1;
+                    int ns = 0;
+                    if (nq_celt_sink_side_get(sink.s, f.side, &tag, &ns, &side) != NQ_OK || tag != f.side || ns < 2 * f.n)
+                        throw std::runtime_error("two-phase Opus decoder: redundancy frame accounting");
+                }
+                if (f.n > 120) throw std::runtime_error("two-phase Opus decoder: unexpected fade length");
+                for (int i = 0; i < f.n; i++) {
+                    const float w = window[i] * window[i];
+                    switch (f.kind) {
+                    case nq_phase1_fixup::CeltToSilk:
+                        if (float *o = at(f.pos + i))
+                            for (int c = 0; c < ch; c++) o[c] = side[size_t(i) * ch + c];
+                        if (float *o = at(f.pos + f.n + i))
+                            for (int c = 0; c < ch; c++) o[c] = w * o[c] + (1.f - w) * side[size_t(f.n + i) * ch + c];
+                        break;
+                    case nq_phase1_fixup::SilkToCelt:
+                        if (float *o = at(f.pos + f.size - f.n + i))
+                            for (int c = 0; c < ch; c++) o[c] = w * side[size_t(f.n + i) * ch + c] + (1.f - w) * o[c];
+                        break;
+                    case nq_phase1_fixup::Transition:
+                        if (float *o = at(f.pos + i))
+                            for (int c = 0; c < ch; c++) o[c] = 0.f;
+                        if (float *o = at(f.pos + f.n + i))
+                            for (int c = 0; c < ch; c++) o[c] = w * o[c];
+                        break;
+                    case nq_phase1_fixup::TransitionShort:
+                        if (float *o = at(f.pos + i))
+                            for (int c = 0; c < ch; c++) o[c] = w * o[c];
+                        break;
+                    }
+                }
+            }
+        }
         // header gain: opusfile programs OPUS_SET_GAIN with OpusHead.output_gain (Q8 dB, default
         // OP_HEADER_GAIN), opus_decode_frame scales by celt_exp2(6.48814081e-4f * gain)
         int gainQ8 = header->output_gain;
@@ -446,11 +502,12 @@ private:
             for (size_t i = 0; i < size_t(totalSamples) * ch; i++) out[i] = out[i] * gain;
         }
         if (st.saw_silk) {
-            // hybrid file: + the SILK layer, which phase 1 decoded, trimmed and scaled by the header gain
-            // already (opus_decoder_clean.c:553-560: pcm = celt + silk / 32768; the sum is linear)
-            if (cpuPcm.size() != size_t(totalSamples) * ch)
+            // + the SILK share, which phase 1 decoded, faded, trimmed and scaled by the header gain
+            // already (opus_decoder_clean.c:553-560: pcm = celt + silk / 32768, then the fades, then the gain)
+            if (cpuStart * ch + int64_t(cpuPcm.size()) != totalSamples * ch)
                 throw std::runtime_error("two-phase Opus decoder: sample accounting does not match opusfile's");
-            for (size_t i = 0; i < cpuPcm.size(); i++) out[i] = out[i] + cpuPcm[i];
+            float *o = out + size_t(cpuStart) * ch;
+            for (size_t i = 0; i < cpuPcm.size(); i++) o[i] = o[i] + cpuPcm[i];
         }
         g_last_timing[0] = t1 - t0;
         g_last_timing[1] = t2 - t1;

@@ -15,13 +15,25 @@ void nq_phase1_frame_tap(const void *celt_decoder, const float *freq, int CC, in
 /* The CELT decoder state `celt_decoder` is being cleared: OPUS_RESET_STATE (celt_decoder_clean.c:846-859)
  * or its initialisation (:137).  The stream's next frame starts from a reset decoder. */
 void nq_phase1_reset_tap(const void *celt_decoder);
-/* silk_Decode is about to run for a packet of coding mode `mode` (MODE_SILK_ONLY 1000 / MODE_HYBRID
- * 1001), the previous packet's having been `prev_mode` (0: none yet). */
+/* opus_decode_frame starts on a packet frame (opus_decoder_clean.c:262-266): `audiosize` samples of
+ * this OpusDecoder's output, coding mode `mode` (MODE_SILK_ONLY 1000 / MODE_HYBRID 1001 /
+ * MODE_CELT_ONLY 1002), the previous frame's having been `prev_mode` (0: none yet). */
+void nq_phase1_frame_begin(const void *opus_decoder, int audiosize, int mode, int prev_mode);
+/* silk_Decode is about to run for a packet of coding mode `mode`. */
 void nq_phase1_note_silk(int mode, int prev_mode);
 /* opus_decode_frame is about to call celt_decode_with_ec: with or without packet data (NULL: loss
- * concealment), for `frame_size` samples (the 5 ms redundancy frames and the 2.5 ms fade-out frame
- * of a mode switch are such calls). */
-void nq_phase1_note_celt_call(int has_data, int frame_size, int mode, int prev_mode);
+ * concealment, which the bundled decoder has no defined behaviour for), for `frame_size` samples.
+ * pcm_arg / data_arg: the call's own argument texts, which tell the three call sites apart --
+ * "redundant_audio": a 5 ms redundancy frame (:485 CELT -> SILK, :540 SILK -> CELT, see celt_to_silk);
+ * data "silence": the 2.5 ms fade-out frame of a hybrid -> SILK switch (:513); else the frame itself. */
+void nq_phase1_note_celt_call(int has_data, int frame_size, int mode, int prev_mode, const char *pcm_arg,
+                              const char *data_arg, int celt_to_silk);
+/* smooth_fade is about to run over `overlap` samples of the current frame (`audiosize` samples long).
+ * in1_arg, the text of its first argument, names the call site: "pcm + ..." :542 the frame's last
+ * 2.5 ms fade into the second half of the redundancy frame (SILK -> CELT); "redundant_audio + ..."
+ * :552 (CELT -> SILK: the first 2.5 ms ARE the redundancy frame's, the next 2.5 ms fade from it);
+ * "pcm_transition + ..." :561 / "pcm_transition" :572 a switch without redundancy. */
+void nq_phase1_fade_tap(const char *in1_arg, int audiosize, int overlap);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "nq_celt_device_count", "nq_celt_launch_count", "nq_celt_host_alloc", "nq_celt_host_free",
     "nq_celt_synth_batch_device", "nq_celt_synth_batch_device_ms", "nq_celt_synth_batch_host",
     "nq_celt_synth_batch_host_multi", "nq_celt_multi_release", "nq_celt_post_batch_device", "nq_celt_post_segments_device", "nq_celt_decode_batch_host",
-    "nq_celt_sink_create", "nq_celt_sink_destroy", "nq_celt_sink_last_error", "nq_celt_sink_push",
+    "nq_celt_sink_create", "nq_celt_sink_destroy", "nq_celt_sink_last_error", "nq_celt_sink_push", "nq_celt_sink_push_at", "nq_celt_sink_side_count", "nq_celt_sink_side_get",
     "nq_celt_sink_pending_frames", "nq_celt_sink_pending_samples", "nq_celt_sink_flush", "nq_celt_sink_reset", "nq_celt_sink_reset_stream", "nq_celt_sink_set_destination",
     "nq_celt_sink_flush_pinned", "nq_celt_sink_flush_many", "nq_celt_sink_begin_upload", "nq_celt_sink_trim_pool", "nq_celt_ctx_device", "nq_celt_ctx_stream", "nq_celt_sink_attach", "nq_celt_sink_finish",
     "nq_clt_mdct_backward", "nq_clt_mdct_backward_B1_C2", "nq_celt_mdct_backward_host",

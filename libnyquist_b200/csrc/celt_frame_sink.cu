@@ -47,7 +47,8 @@ struct Block {
     float *coef = nullptr;                 // [kBlockFrames][D][960]  pinned
     uint8_t *flags = nullptr;              // [kBlockFrames][streams] pinned
     nq_celt_post_frame *post = nullptr;    // [kBlockFrames][streams] pinned
-    int D = 0, streams = 0;
+    long long *dest = nullptr;             // [kBlockFrames] first output sample of the frame, -1: right after the frame before it
+    int D = 0, streams = 0;                //                 -2: a side frame (its PCM is kept aside, nq_celt_sink_side_*)
 };
 
 // Page-locking host memory costs ~0.3 ms per MB, more than phase 2 itself for a typical file, so
@@ -71,6 +72,7 @@ void free_block(Block &b)
     nq_celt_host_free(b.coef);
     nq_celt_host_free(b.flags);
     nq_celt_host_free(b.post);
+    free(b.dest);
     b = Block();
 }
 
@@ -103,7 +105,8 @@ bool take_block(int D, int streams, Block *out)
     b.coef = (float *)nq_celt_host_alloc(sizeof(float) * kBlockFrames * D * kFrame);
     b.flags = (uint8_t *)nq_celt_host_alloc((size_t)kBlockFrames * streams);
     b.post = (nq_celt_post_frame *)nq_celt_host_alloc(sizeof(nq_celt_post_frame) * kBlockFrames * streams);
-    if (!b.coef || !b.flags || !b.post) {
+    b.dest = (long long *)malloc(sizeof(long long) * kBlockFrames);
+    if (!b.coef || !b.flags || !b.post || !b.dest) {
         free_block(b);
         return false;
     }
@@ -186,7 +189,10 @@ struct nq_celt_sink {
     nq_celt_ctx *ctx = nullptr;
     float *dst = nullptr;
     long long skip = 0, dst_samples = 0;
-    long long produced = 0;          // decoded samples per channel so far (worker)
+    long long produced = 0;          // end of the last frame placed in the output timeline (worker)
+    bool placed = false;             // some frame carried an explicit destination or was a side frame
+    struct Side { long long tag; int nsamples; std::vector<float> pcm; };
+    std::vector<Side> sides;         // side frames in push order (streaming mode)
     std::thread worker;
     std::mutex mu;
     std::condition_variable cv;
@@ -315,24 +321,51 @@ void worker_main(nq_celt_sink *s)
             }
             if (rc == NQ_OK) rc = decode_block(s, s->ctx, job.block, job.nframes, s->out);
             if (rc == NQ_OK) {
-                // decoded sample p (per channel) lands at dst[(p - skip) * channels] if inside the window
-                long long a = s->produced, b = s->produced + n;
-                long long lo = a > s->skip ? a : s->skip;
-                long long hi = b < s->skip + s->dst_samples ? b : s->skip + s->dst_samples;
-                if (hi > lo) {
-                    float *dst;
-                    {   // the destination may be announced after the attach (nq_celt_sink_set_destination)
+                // decoded sample p (per channel) lands at dst[(p - skip) * channels] if inside the window;
+                // a frame sits right after the one before it unless it names its own place in the
+                // output timeline (files that switch coding modes: the CELT decoder is not called
+                // for every stretch of the output, and some of its frames are side frames)
+                float *dst = nullptr;
+                auto place = [&](long long a, const float *src, long long n) {   // samples [a, a + n) of the timeline
+                    long long lo = a > s->skip ? a : s->skip;
+                    long long hi = a + n < s->skip + s->dst_samples ? a + n : s->skip + s->dst_samples;
+                    if (hi <= lo) return;
+                    if (!dst) {   // the destination may be announced after the attach (nq_celt_sink_set_destination)
                         std::unique_lock<std::mutex> lk(s->mu);
                         s->cv.wait(lk, [&] { return s->dst != nullptr || s->stop; });
                         dst = s->dst;
+                        if (!dst) {
+                            rc = sink_fail(s, NQ_INVALID_STATE, "finished without a destination");
+                            return;
+                        }
                     }
-                    if (dst)
-                        memcpy(dst + (size_t)(lo - s->skip) * s->channels, s->out + (size_t)(lo - a) * s->channels,
-                               sizeof(float) * (size_t)(hi - lo) * s->channels);
-                    else
-                        rc = sink_fail(s, NQ_INVALID_STATE, "finished without a destination");
+                    memcpy(dst + (size_t)(lo - s->skip) * s->channels, src + (size_t)(lo - a) * s->channels,
+                           sizeof(float) * (size_t)(hi - lo) * s->channels);
+                };
+                bool plain = true;
+                for (long long f = 0; f < job.nframes && plain; f++) plain = job.block.dest[f] == -1;
+                if (plain) {
+                    place(s->produced, s->out, n);
+                    s->produced += n;
+                } else {
+                    long long off = 0;
+                    for (long long f = 0; f < job.nframes && rc == NQ_OK; f++) {
+                        const long long N = job.block.post[f * s->streams].N, d = job.block.dest[f];
+                        const float *src = s->out + (size_t)off * s->channels;
+                        if (d <= -2) {
+                            nq_celt_sink::Side sd;
+                            sd.tag = -2 - d;
+                            sd.nsamples = (int)N;
+                            sd.pcm.assign(src, src + (size_t)N * s->channels);
+                            s->sides.push_back(std::move(sd));
+                        } else {
+                            const long long a = d >= 0 ? d : s->produced;
+                            place(a, src, N);
+                            s->produced = a + N;
+                        }
+                        off += N;
+                    }
                 }
-                s->produced = b;
             }
         }
         recycle_block(job.block);
@@ -427,7 +460,17 @@ const char *nq_celt_sink_last_error(const nq_celt_sink *s) { return s ? s->err :
 int nq_celt_sink_push(nq_celt_sink *s, int stream, const float *freq, int CC, int N, int shortBlocks,
                       const nq_celt_post_frame *post)
 {
+    return nq_celt_sink_push_at(s, stream, freq, CC, N, shortBlocks, post, -1);
+}
+
+int nq_celt_sink_push_at(nq_celt_sink *s, int stream, const float *freq, int CC, int N, int shortBlocks,
+                         const nq_celt_post_frame *post, int64_t dest)
+{
     if (!s || !freq || !post) return NQ_BAD_ARG;
+    if (dest != -1) {
+        if (s->streams != 1) return sink_fail(s, NQ_UNIMPLEMENTED, "frames with a place of their own: single-stream files only");
+        if (!s->ctx || s->upload) return sink_fail(s, NQ_INVALID_STATE, "frames with a place of their own need streaming mode (nq_celt_sink_attach)");
+    }
     if (stream < 0 || stream >= s->streams) return sink_fail(s, NQ_BAD_ARG, "stream index out of range");
     const int nch = stream < s->coupled ? 2 : 1;
     if (CC != nch) return sink_fail(s, NQ_BAD_ARG, "channel count of the frame does not match the stream (coupled = 2, mono = 1)");
@@ -460,6 +503,7 @@ int nq_celt_sink_push(nq_celt_sink *s, int stream, const float *freq, int CC, in
     // a frame with one short block IS a long block of the same size (celt_decoder_clean.c:273-284)
     b.flags[fi * s->streams + stream] = (uint8_t)((shortBlocks > 1 ? 1 : 0) | ((3 - LM) << 1) | (after_reset ? 8 : 0));
     b.post[fi * s->streams + stream] = *post;
+    if (stream == 0) b.dest[fi] = dest;
     std::lock_guard<std::mutex> lk(s->push_mu);
     s->pushed[stream] = f + 1;
     // streaming: hand every complete block to the worker
@@ -893,10 +937,22 @@ int nq_celt_sink_attach(nq_celt_sink *s, nq_celt_ctx *ctx, float *dst, int64_t s
     s->skip = skip_samples;
     s->dst_samples = dst_samples;
     s->produced = 0;
+    s->sides.clear();
     s->first_block = 0;
     s->stop = false;
     s->worker_rc = NQ_OK;
     s->worker = std::thread(worker_main, s);
+    return NQ_OK;
+}
+
+int nq_celt_sink_side_count(const nq_celt_sink *s) { return s ? (int)s->sides.size() : 0; }
+
+int nq_celt_sink_side_get(const nq_celt_sink *s, int i, int64_t *tag, int *nsamples, const float **pcm)
+{
+    if (!s || i < 0 || i >= (int)s->sides.size()) return NQ_BAD_ARG;
+    if (tag) *tag = s->sides[i].tag;
+    if (nsamples) *nsamples = s->sides[i].nsamples;
+    if (pcm) *pcm = s->sides[i].pcm.data();
     return NQ_OK;
 }
 

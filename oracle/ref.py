@@ -211,6 +211,27 @@ def encode_mode_switch(pcm: np.ndarray, mode_a: int, mode_b: int, switch_frame: 
     return out[:got].tobytes()
 
 
+def encode_mode_schedule(pcm: np.ndarray, first_mode: int, schedule, bitrate: int = 40000) -> bytes:
+    """A file that walks through several coding modes: schedule = [(frame, mode), ...]."""
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    n, ch = pcm.shape
+    assert n % FRAME == 0 and ch in (1, 2)
+    cap = 1 << 22
+    out = np.zeros(cap, np.uint8)
+    frames = np.asarray([f for f, _ in schedule], np.int32)
+    modes = np.asarray([m for _, m in schedule], np.int32)
+    L = lib()
+    L.nqref_encode_mode_schedule.restype = C.c_long
+    L.nqref_encode_mode_schedule.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_long]
+    got = L.nqref_encode_mode_schedule(pcm.ctypes.data_as(C.c_void_p), n, ch, int(bitrate), int(first_mode),
+                                       frames.ctypes.data_as(C.c_void_p), modes.ctypes.data_as(C.c_void_p), len(schedule),
+                                       out.ctypes.data_as(C.c_void_p), cap)
+    if got < 0:
+        raise RuntimeError(f"reference encoder failed: {got}")
+    return out[:got].tobytes()
+
+
 def encode_forced_mode(pcm: np.ndarray, mode: int, bitrate: int = 32000) -> bytes:
     """The reference's own encoder (VOIP application) forced into one coding mode with the private
     OPUS_SET_FORCE_MODE ctl: test files for the SILK / hybrid branches of opus_decode_frame

@@ -356,6 +356,8 @@ static int put_page(ogg_stream_state *os, int flush, unsigned char *out, long ca
  * (opus_private.h:90-96), with the VOIP application -- test files for the SILK / hybrid paths of
  * opus_decode_frame (opus_decoder_clean.c:340-600). */
 static int g_switch_frame = -1, g_switch_mode = 0;   /* nqref_encode_mode_switch: from this frame on, that mode */
+static const int *g_sched_frames = NULL, *g_sched_modes = NULL;   /* nqref_encode_mode_schedule: several switches */
+static int g_sched_n = 0;
 
 static long encode_ogg(const float *pcm, long nsamples, int channels, int bitrate, int force_mode,
                        unsigned char *out, long cap)
@@ -406,6 +408,11 @@ static long encode_ogg(const float *pcm, long nsamples, int channels, int bitrat
     for (f = 0; f < nframes; f++) {
         int n;
         if (f == g_switch_frame) opus_multistream_encoder_ctl(enc, OPUS_SET_FORCE_MODE(g_switch_mode));
+        for (i = 0; i < g_sched_n; i++)
+            if (f == g_sched_frames[i]) {   /* (SILK-only needs a SILK bandwidth, or the encoder makes it hybrid) */
+                opus_multistream_encoder_ctl(enc, OPUS_SET_FORCE_MODE(g_sched_modes[i]));
+                opus_multistream_encoder_ctl(enc, OPUS_SET_BANDWIDTH(g_sched_modes[i] == MODE_SILK_ONLY ? OPUS_BANDWIDTH_WIDEBAND : OPUS_BANDWIDTH_FULLBAND));
+            }
         n = opus_multistream_encode_float(enc, pcm + f * FRAME * channels, FRAME, pkt, (opus_int32)sizeof pkt);
         if (n < 0) return -4;
         memset(&op, 0, sizeof op);
@@ -445,6 +452,19 @@ NQREF_API long nqref_encode_mode_switch(const float *pcm, long nsamples, int cha
     g_switch_mode = mode_b;
     n = encode_ogg(pcm, nsamples, channels, bitrate, mode_a, out, cap);
     g_switch_frame = -1;
+    return n;
+}
+
+/* A file that walks through several coding modes: from frame frames[i] on, mode modes[i]. */
+NQREF_API long nqref_encode_mode_schedule(const float *pcm, long nsamples, int channels, int bitrate, int first_mode,
+                                          const int *frames, const int *modes, int nswitch, unsigned char *out, long cap)
+{
+    long n;
+    g_sched_frames = frames;
+    g_sched_modes = modes;
+    g_sched_n = nswitch;
+    n = encode_ogg(pcm, nsamples, channels, bitrate, first_mode, out, cap);
+    g_sched_n = 0;
     return n;
 }
 

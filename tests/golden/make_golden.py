@@ -182,6 +182,17 @@ def main():
                "transient_records": int(sum(r["B"] == 8 for r in recs8)),
                "reference_pcm_sha256": hashlib.sha256(out8.tobytes()).hexdigest()},
               open(f"{HERE}/surround8.json", "w"), indent=1)
+    make_mode_files()
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+def make_mode_files():
+    import hashlib
+    import json
+    """hybrid.opus, silk_stereo.opus, modeswitch.opus + modes.json (python make_golden.py --modes-only
+    regenerates just these)."""
+    fs = 48000
     # ---- hybrid / SILK-only files (the coding modes of opus_decode_frame besides CELT-only) ----
     n = 960 * 150
     t = np.arange(n) / fs
@@ -205,10 +216,27 @@ def main():
         info[name] = {"samples_per_channel": int(out.shape[0]), "channels": int(out.shape[1]), "celt_frames": len(recs),
                       "transient_frames": int(sum(r["B"] > 1 for r in recs)),
                       "reference_pcm_sha256": hashlib.sha256(out.tobytes()).hexdigest()}
+    # ---- a file that walks through the coding modes: CELT -> hybrid -> SILK -> hybrid -> CELT -> SILK ->
+    # CELT -> hybrid.  The encoder puts a 5 ms redundancy frame next to every switch from / to CELT-only
+    # and the decoder cross-fades it in (opus_decoder_clean.c:478-487, :530-555); hybrid -> SILK makes the
+    # decoder add a 2.5 ms CELT fade-out frame (:507-514) ----
+    S, H, Cm = ref.MODE_SILK_ONLY, ref.MODE_HYBRID, ref.MODE_CELT_ONLY
+    sched = [(20, H), (40, S), (60, H), (80, Cm), (100, S), (120, Cm), (135, H)]
+    data = ref.encode_mode_schedule(speech, Cm, sched, 40000)
+    open(f"{HERE}/modeswitch.opus", "wb").write(data)
+    out, recs = ref.decode_bytes(data, record=True)
+    sizes = [int(r["coef"].shape[1]) for r in recs]
+    assert sizes.count(240) >= 5 and sizes.count(120) >= 1, sizes
+    info["modeswitch"] = {"samples_per_channel": int(out.shape[0]), "channels": int(out.shape[1]), "celt_frames": len(recs),
+                          "transient_frames": int(sum(r["B"] > 1 for r in recs)),
+                          "redundancy_frames": sizes.count(240), "fade_out_frames": sizes.count(120),
+                          "schedule": [[f, m] for f, m in sched],
+                          "reference_pcm_sha256": hashlib.sha256(out.tobytes()).hexdigest()}
     json.dump(info, open(f"{HERE}/modes.json", "w"), indent=1)
-    for f in sorted(os.listdir(HERE)):
-        print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
 if __name__ == "__main__":
-    main()
+    if "--modes-only" in sys.argv:
+        make_mode_files()
+    else:
+        main()

@@ -215,24 +215,62 @@ def test_hybrid_file_celt_layer_on_the_gpu_plus_silk_layer_of_phase_1(twophase):
             assert hashlib.sha256(got.tobytes()).hexdigest() == info[name]["reference_pcm_sha256"]
 
 
-@pytest.mark.parametrize("a,b", [("hybrid", "celt"), ("celt", "hybrid")])
-def test_mode_switching_file_is_refused_not_misdecoded(twophase, tmp_path, a, b):
-    """A switch between coding modes makes opus_decode_frame decode 5 ms redundancy frames into side
-    buffers and cross-fade them in (opus_decoder_clean.c:478-487, :570-600) -- not a plain sum of
-    layers.  Load must fail loudly; the reference itself decodes the file."""
+def _switch_signal(n, channels, seed=1):
+    t = np.arange(n) / 48000
+    rng = np.random.default_rng(seed)
+    sig = (0.2 * np.sin(2 * np.pi * 180 * t) * (1 + 0.5 * np.sin(2 * np.pi * 2.3 * t)) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    sig[::7200] += 0.5                                   # a few clicks: transient frames
+    return np.stack([sig, np.roll(sig, 41) * 0.7], 1)[:, :channels].copy()
+
+
+MODES = {"silk": 1000, "hybrid": 1001, "celt": 1002}     # opus_private.h:90-92
+
+
+@pytest.mark.parametrize("a,b,channels", [("hybrid", "celt", 2), ("celt", "hybrid", 2), ("silk", "celt", 2), ("celt", "silk", 2),
+                                          ("hybrid", "silk", 2), ("silk", "hybrid", 2), ("celt", "hybrid", 1), ("silk", "celt", 1)])
+def test_mode_switching_file_matches_the_reference(twophase, tmp_path, a, b, channels):
+    """a switch between coding modes makes opus_decode_frame decode a
+    5 ms redundancy frame into a side buffer and cross-fade it in (opus_decoder_clean.c:478-487,
+    :530-555), reset the CELT decoder (:495-497, :536-538) and, from hybrid to SILK, add a 2.5 ms CELT
+    fade-out frame (:507-514).  Phase 2 decodes those frames in sequence (side frames, reset flags,
+    frames with their own place in the output), the loader applies the same fades to its PCM."""
     if not ref.available():
         pytest.skip("oracle/_ref (compiled reference) not present")
-    modes = {"hybrid": ref.MODE_HYBRID, "celt": ref.MODE_CELT_ONLY}
-    n = 960 * 60
-    t = np.arange(n) / 48000
-    sig = (0.2 * np.sin(2 * np.pi * 180 * t) + 0.05 * np.random.default_rng(1).standard_normal(n)).astype(np.float32)
-    data = ref.encode_mode_switch(np.stack([sig, sig * 0.7], 1), modes[a], modes[b], 30)
+    data = ref.encode_mode_switch(_switch_signal(960 * 60, channels), MODES[a], MODES[b], 30)
     path = tmp_path / "switch.opus"
     path.write_bytes(data)
     want, recs = ref.decode_bytes(data, record=True)
-    assert want.shape[1] == 2 and any(r["coef"].shape[1] == 240 for r in recs)   # the redundancy frames are there
-    got, *_ = load(twophase, str(path))
-    assert got is None
+    sizes = [r["coef"].shape[1] for r in recs]
+    if "celt" in (a, b):
+        assert 240 in sizes                                  # the redundancy frame is there
+    # (hybrid -> SILK with its 2.5 ms fade-out frame: the fixture of the next test; this generator keeps the
+    # full bandwidth after the switch, which makes the encoder stay hybrid)
+    got, ch, sr, tm, wall = load(twophase, str(path))
+    assert got is not None and ch == channels and got.shape == want.shape
+    err = float(np.abs(got.astype(np.float64) - want).max())
+    assert err <= 1e-5 and snr_db(want, got) >= 100.0, (a, b, err)
+    assert float(np.abs(want).max()) > 0.1
+
+
+def test_mode_walk_fixture_matches_the_reference(twophase):
+    """tests/golden/modeswitch.opus (make_golden.py): CELT -> hybrid -> SILK -> hybrid -> CELT -> SILK ->
+    CELT -> hybrid in one file: 7 redundancy frames, 1 fade-out frame, 110 ordinary CELT frames."""
+    import hashlib
+    import json
+    from conftest import GOLDEN
+    info = json.load(open(os.path.join(GOLDEN, "modes.json")))["modeswitch"]
+    path = os.path.join(GOLDEN, "modeswitch.opus")
+    got, ch, sr, tm, wall = load(twophase, path)
+    assert got is not None and (ch, sr) == (2, 48000) and got.shape == (info["samples_per_channel"], 2)
+    if not ref.available():
+        pytest.skip("oracle/_ref (compiled reference) not present: shape checked only")
+    want, recs = ref.decode_file(path, record=True)
+    assert hashlib.sha256(want.tobytes()).hexdigest() == info["reference_pcm_sha256"]
+    sizes = [r["coef"].shape[1] for r in recs]
+    assert (len(recs), sizes.count(240), sizes.count(120)) == (info["celt_frames"], info["redundancy_frames"], info["fade_out_frames"])
+    err = float(np.abs(got.astype(np.float64) - want).max())
+    assert err <= 1e-5 and snr_db(want, got) >= 100.0, err
+    print(f"\nmodeswitch.opus: Load {wall * 1e3:.1f} ms, max |err| {err:.2e}")
 
 
 def test_two_phase_load_errors_like_the_reference(twophase, tmp_path):

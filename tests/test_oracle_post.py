@@ -128,5 +128,9 @@ def test_hybrid_and_silk_files_reference_decode_is_pinned():
         assert pcm.shape == (meta["samples_per_channel"], meta["channels"]) and len(recs) == meta["celt_frames"]
         assert hashlib.sha256(pcm.tobytes()).hexdigest() == meta["reference_pcm_sha256"]
         assert sum(r["B"] > 1 for r in recs) == meta["transient_frames"]
+        if name == "modeswitch":   # a walk through the modes: full-band CELT frames, 5 ms redundancy frames, a fade-out frame
+            sizes = [r["coef"].shape[1] for r in recs]
+            assert (sizes.count(240), sizes.count(120)) == (meta["redundancy_frames"], meta["fade_out_frames"])
+            continue
         for r in recs:
             assert r["coef"].shape == (2, 960) and not r["coef"][:, :320].any() and r["coef"][:, 320:].any()
