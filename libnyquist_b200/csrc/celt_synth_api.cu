@@ -271,6 +271,11 @@ int plan_layout(const Layout &L, int num_sms, long long nframes, SynthParams *pp
             vec = d != 255 && d < 2 * L.coupled && (d & 1) == 0 && L.mapping[c + 1] == d + 1;
         }
         p.store_shape = p.store_threads == 0 ? 3 : (muted ? 2 : (vec ? 0 : 1));
+        // a lone mono stream (odd number of mono streams: 5.0, 6.1, ...): its warp synthesises frame PAIRS, the
+        // time it saves goes to the group's other warps.  Groups of two warps (3.0) do not gain: with one coupled
+        // warp per group the coupled stream's own latency sets the pace (measured 0.64 -> 0.62; 5.0: 0.68 -> 0.73)
+        p.lone_pairs = (nmono & 1) && nslots >= 3 ? 1 : 0;
+        if (const char *e = getenv("NQ_LONE_PAIRS")) p.lone_pairs = (nmono & 1) && atoi(e) ? 1 : 0;
         for (int c = 0; c < L.C; c++) {
             const int d = L.mapping[c];
             if (d == 255) p.chan_src[c] = 0xffffu;   // muted channel, opus_multistream_decoder.c:291-299

@@ -124,7 +124,8 @@ struct __align__(16) WarpSmem {
     // group's synthesis warps and its store warp(s), and the ring through which the group's first
     // warp publishes the runs it claims.
     unsigned long long full;          // mbarrier: every synthesis warp's plane of the frame is complete
-    unsigned long long empty;         // mbarrier: the store warps are done reading the planes
+    unsigned long long empty;         // (low 32 bits) a COUNTER: frames x store warps done reading the planes.  Not an mbarrier: the
+                                      // warp of a lone mono stream hands over two frames at a time, and a parity wait cannot skip a phase
     unsigned long long pad_;
     unsigned long long claim[4];      // (run << 8 | sequence number), see celt_synth_kernel
 };
@@ -178,21 +179,26 @@ struct StoreCtx {
     int T;                 // store threads of the group
     uint32_t planes;       // shared-memory byte address of the group's first plane
     unsigned mute;         // bit j: element j belongs to a silent output channel
+    unsigned lone;         // bit j: element j comes from the group's lone mono stream (its plane holds frame pairs)
     int shape;             // store-loop shape, see group_store_frame (uniform over the group)
 };
 
 // A synthesis warp's view of its group.
 struct GroupLink {
-    unsigned long long *full, *empty;
+    unsigned long long *full;
+    volatile unsigned *stored;   // the group's counter of finished store passes (frames x store warps)
     uint32_t nstored;      // frames handed to the store warps so far
+    uint32_t store_warps;  // store warps of the group: each counts a frame once
     bool pending;          // the store pass of the last one may still be reading this warp's plane
 };
 
-// Called before anything is written to ws.x (the plane of the previous stored frame).
+// Called before anything is written to ws.x (the plane of the previous stored frame(s)): every frame
+// this warp has handed over must have been stored.
 __device__ __forceinline__ void group_wait_plane_free(GroupLink &g)
 {
     if (g.pending) {
-        mbar_wait(g.empty, (g.nstored - 1) & 1);
+        const unsigned need = g.nstored * g.store_warps;
+        while ((int)(*g.stored - need) < 0) {}
         g.pending = false;
     }
 }
@@ -218,7 +224,8 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
 // General form (shape 3), for channel counts no store-thread count divides evenly (4*T2 % C != 0 for
 // every usable T2: many duplicated output channels on few streams): every float4 of the output frame
 // is gathered element by element, channel and sample re-derived per element.  Slow, correct, rare.
-static __device__ __noinline__ void group_store_frame_general(const SynthParams &p, uint32_t planes, int tg, int T, float *frame_out, int nsamples)
+static __device__ __noinline__ void group_store_frame_general(const SynthParams &p, uint32_t planes, int tg, int T, float *frame_out, int nsamples,
+                                                              int lone_slot, int col)
 {
     const int C = p.C, nq4 = (nsamples / 4) * C;
     float4 *dst = reinterpret_cast<float4 *>(frame_out);
@@ -228,17 +235,21 @@ static __device__ __noinline__ void group_store_frame_general(const SynthParams 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const unsigned sc = p.chan_src[c];
-            v[j] = sc == 0xffffu ? 0.f : lds_f32(planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + (sc & 1) * 4 + n * 8);
+            const unsigned sub = (int)(sc >> 1) == lone_slot ? (unsigned)col : (sc & 1);   // a lone mono stream's plane: column = frame of the pair
+            v[j] = sc == 0xffffu ? 0.f : lds_f32(planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + sub * 4 + n * 8);
             if (++c == C) { c = 0; n++; }
         }
         __stcs(dst + q, make_float4(v[0], v[1], v[2], v[3]));
     }
 }
 
-__device__ __forceinline__ void group_store_frame(const StoreCtx &g, uint32_t base, float *frame_out, int niter)
+// col: which column of a lone mono stream's plane this frame is (its warp synthesises frame pairs)
+__device__ __forceinline__ void group_store_frame(const StoreCtx &g, uint32_t base, float *frame_out, int niter, int col)
 {
     float4 *dst = reinterpret_cast<float4 *>(frame_out) + g.q0;
-    uint32_t a0 = base + g.src[0], a1 = base + g.src[1], a2 = base + g.src[2], a3 = base + g.src[3];
+    const unsigned lm = col ? g.lone : 0u;
+    uint32_t a0 = base + g.src[0] + ((lm & 1) ? 4u : 0u), a1 = base + g.src[1] + ((lm & 2) ? 4u : 0u),
+             a2 = base + g.src[2] + ((lm & 4) ? 4u : 0u), a3 = base + g.src[3] + ((lm & 8) ? 4u : 0u);
     const uint32_t step = g.step;
     const int T2 = g.T2;
     if (g.shape == 0) {
@@ -276,8 +287,10 @@ __device__ __forceinline__ void group_store_frame(const StoreCtx &g, uint32_t ba
 // after_generic_writes: ws.in was WRITTEN with ordinary stores since the last copy landed (a short
 // frame parks its samples there): a proxy fence orders those stores before the copy engine's writes
 // (the pattern of a TMA store after shared-memory writes: fence in every writer, barrier, one issuer).
+// row2: where the second row sits relative to the first, in floats: kFrame (the other channel of the
+// frame) or D * kFrame (the same channel of the NEXT frame: a mono stream's frame pair).
 __device__ __forceinline__ void prefetch_rows(const SynthParams &p, WarpSmem &ws, int lane, long long fnext, int cb, int rows,
-                                              bool after_generic_writes)
+                                              bool after_generic_writes, long long row2 = kFrame)
 {
     if (after_generic_writes) {   // every lane fences its own stores, then the warp meets, then lane 0 issues
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -287,7 +300,7 @@ __device__ __forceinline__ void prefetch_rows(const SynthParams &p, WarpSmem &ws
         const float *src = (fnext < 0 ? p.halo_coef : p.coef + fnext * p.D * kFrame) + cb * kFrame;
         mbar_expect_tx(&ws.bar, rows * kFrame * 4);
         tma_load_row(ws.in, src, kFrame * 4, &ws.bar);
-        if (rows == 2) tma_load_row(ws.in + kInRowFloats, src + kFrame, kFrame * 4, &ws.bar);
+        if (rows == 2) tma_load_row(ws.in + kInRowFloats, src + row2, kFrame * 4, &ws.bar);
     }
 }
 
@@ -335,13 +348,18 @@ __device__ __forceinline__ void stage1_common(const FastTables &tb, WarpSmem &ws
 // Two mono streams that share a warp switch blocks independently; when they disagree the frame
 // goes through both paths and each keeps only its own channel.
 template <int kModeT>
+// lone (group mode): this warp carries a LONE mono stream and treats it like kModeMono does -- `lone`
+// consecutive frames (1 or 2) as its channels, tail in slot 0 -- while still computing two channels
+// (the second one of a single frame is scratch); 0: an ordinary warp of the group.
 __device__ __forceinline__ void long_stage2(const SynthParams &p, WarpSmem &ws, int lane, long long off, int cb, int nch,
-                                            bool store, const float (&w4)[4], int vmask)
+                                            bool store, const float (&w4)[4], int vmask, int lone = 0)
 {
     constexpr bool kPaired = kModeT == kModeGroupPaired;
     constexpr int kMode = kPaired ? kModeGroup : kModeT;
     constexpr bool kStereo = kMode == kModeStereo;
     if (!kPaired) vmask = 3;
+    const bool mono = kMode == kModeMono || (kMode == kModeGroup && lone > 0);   // (compile time except in group mode)
+    const int mframes = kMode == kModeMono ? nch : lone;                          // frames of a mono item
     constexpr float post_re[16] = {NQ_POST16_RE};
     constexpr float post_im[16] = {NQ_POST16_IM};
 
@@ -353,7 +371,7 @@ __device__ __forceinline__ void long_stage2(const SynthParams &p, WarpSmem &ws, 
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
         if (ch < nch) {
-            told[ch] = *reinterpret_cast<const float2 *>(ws.tail + (kMode == kModeMono ? 0 : ch * kHalfOvl) + 58 - 2 * k1);
+            told[ch] = *reinterpret_cast<const float2 *>(ws.tail + (mono ? 0 : ch * kHalfOvl) + 58 - 2 * k1);
             float2 z[16];
             const float2 *src = ws.x + ch * kXChanF2 + k1;
 #pragma unroll
@@ -373,7 +391,7 @@ __device__ __forceinline__ void long_stage2(const SynthParams &p, WarpSmem &ws, 
         }
     }
     __syncwarp();   // all lanes are done with ws.x and with the old tail
-    if (kMode == kModeMono && nch == 2) {
+    if (mono && mframes == 2) {
         // frame f+1 mirrors against frame f's raw tail: tail[58-2k1], tail[59-2k1] sit in lane 29-k1
         told[1].x = __shfl_sync(kFull, E[0][15], (29 - lane) & 31);
         told[1].y = __shfl_sync(kFull, O[0][15], (29 - lane) & 31);
@@ -381,8 +399,8 @@ __device__ __forceinline__ void long_stage2(const SynthParams &p, WarpSmem &ws, 
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
         if (ch < nch) {
-            if (kMode == kModeMono) {   // one stream: only the LAST frame's tail is kept, in slot 0
-                if (active && ch == nch - 1) *reinterpret_cast<float2 *>(ws.tail + 2 * k1) = make_float2(E[ch][15], O[ch][15]);
+            if (mono) {   // one stream: only the LAST frame's tail is kept, in slot 0
+                if (active && ch == mframes - 1) *reinterpret_cast<float2 *>(ws.tail + 2 * k1) = make_float2(E[ch][15], O[ch][15]);
             } else if (active && (!kPaired || ((vmask >> ch) & 1)))   // raw tail for the next frame: y[900+2k1], y[901+2k1]
                 *reinterpret_cast<float2 *>(ws.tail + ch * kHalfOvl + 2 * k1) = make_float2(E[ch][15], O[ch][15]);
             // TDAC mirror with the previous raw tail [mdct.c:361-377]; m = 2k1 and 2k1+1
@@ -499,10 +517,12 @@ __device__ __forceinline__ void long_stage2(const SynthParams &p, WarpSmem &ws, 
 // trips needs are read before the group's first write (one warp barrier per group).
 template <int kModeT>
 __device__ __forceinline__ void short_stage2(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off, int nch,
-                                             bool store, int vmask)
+                                             bool store, int vmask, int lone = 0)
 {
     constexpr bool kPaired = kModeT == kModeGroupPaired;
     constexpr int kMode = kPaired ? kModeGroup : kModeT;
+    const bool mono = kMode == kModeMono || (kMode == kModeGroup && lone > 0);   // see long_stage2
+    const int mframes = kMode == kModeMono ? nch : lone;
 #ifndef NQ_SHORT_ST
 #define NQ_SHORT_ST 2
 #endif
@@ -516,9 +536,9 @@ __device__ __forceinline__ void short_stage2(const SynthParams &p, const FastTab
     const uint32_t xstep = h ? (uint32_t)-8 : 8u;
     float *st_lo = ws.in + park_index<kMode>(c, 120 * b) + 59 - h, *st_hi = st_lo + 1 + 2 * h;   // trip i: st_lo[-2i], st_hi[2i]
     // kModeMono: c = 1 is the NEXT frame of the same stream; its block 0 follows block 7 of c = 0 (lane - 2)
-    float *tail = ws.tail + (kMode == kModeMono ? 0 : c * kHalfOvl) + 59 - h;   // trip i: tail[-2i]
-    const bool tail_from_smem = b == 0 && (kMode != kModeMono || c == 0);
-    const bool tail_writer = b == 7 && (kMode == kModeMono ? c == nch - 1 : mine);
+    float *tail = ws.tail + (mono ? 0 : c * kHalfOvl) + 59 - h;   // trip i: tail[-2i]
+    const bool tail_from_smem = b == 0 && (!mono || c == 0);
+    const bool tail_writer = b == 7 && (mono ? c == mframes - 1 : mine);
     const float sg = h ? -1.0f : 1.0f;
     const float c1 = h ? NQ_SQRT1_2 : -1.0f, c2 = h ? NQ_SQRT1_2 : 0.0f, c3 = h ? -NQ_SQRT1_2 : 0.0f, c4 = h ? NQ_SQRT1_2 : 1.0f;
     const float2 *wp = tb.wpair + h * 30;
@@ -701,6 +721,9 @@ __device__ __forceinline__ long long group_next_item(const volatile unsigned lon
 // layouts with many narrow groups): it polls their `full` barriers, writes the unit's part of the
 // interleaved frame and releases the planes.  Every unit walks the same runs and frames as the
 // synthesis warps of its group.
+#ifndef NQ_LONE_PAIRS
+#define NQ_LONE_PAIRS 1   // group mode: the warp of a lone mono stream takes two consecutive frames as its two channels
+#endif
 #ifndef NQ_STORE_SLEEP_NS
 #define NQ_STORE_SLEEP_NS 256
 #endif
@@ -719,14 +742,26 @@ __device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem 
     st.step = (uint32_t)(4 * st.T2 / C) * 8u;
     st.niter = tg < st.T2 ? ((kFrame / 4) * C - tg + st.T2 - 1) / st.T2 : 0;
     st.mute = 0;
+    st.lone = 0;
     st.planes = kPlaneOffFloats * 4;   // relative to the group's first slice
     st.shape = p.store_shape;
+    // the group's lone mono stream, if any: its warp synthesises frame PAIRS (celt_synth_kernel), so its
+    // plane holds frame f in column 0 and frame f + 1 in column 1; `second` below follows the same
+    // greedy pairing rule as the synthesis warp
+    int lone_slot = -1, lone_col = 0;
+    if (NQ_LONE_PAIRS && p.lone_pairs)
+        for (int w = 0; w < W; w++)
+            if (p.streams[w].nch == 1) {
+                lone_slot = w;
+                lone_col = p.streams[w].flag_col;
+            }
     {
         int n = (4 * tg) / C, c = (4 * tg) % C;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const unsigned sc = p.chan_src[c];
             if (sc == 0xffffu) st.mute |= 1u << j;
+            else if ((int)(sc >> 1) == lone_slot) st.lone |= 1u << j;
             st.src[j] = sc == 0xffffu ? st.planes : st.planes + (sc >> 1) * (uint32_t)sizeof(WarpSmem) + (sc & 1) * 4 + n * 8;
             if (++c == C) { c = 0; n++; }
         }
@@ -735,9 +770,11 @@ __device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem 
     const long long item_stride = (long long)gridDim.x * G;
     long long item[kMaxStoreUnits] = {}, f[kMaxStoreUnits] = {}, f1[kMaxStoreUnits] = {};
     uint32_t nstored[kMaxStoreUnits] = {}, seq[kMaxStoreUnits] = {};
+    bool second[kMaxStoreUnits] = {};   // the unit's next frame is the second one of a lone mono stream's pair
     WarpSmem *ugws[kMaxStoreUnits] = {};
     int nunits = 0, alive = 0;
     auto start_run = [&](int k) {
+        second[k] = false;
         if (item[k] < p.nruns) {
             seq[k]++;
             run_range(p, item[k], &f[k], &f1[k]);
@@ -769,10 +806,21 @@ __device__ __forceinline__ void group_store_role(const SynthParams &p, WarpSmem 
                 niter = tg < st.T2 ? ((nsamples / 4) * C - tg + st.T2 - 1) / st.T2 : 0;
                 out = p.pcm + p.frame_offset[fr] * C;
             }
+            int col = 0;
+            if (lone_slot >= 0) {
+                if (second[k]) {
+                    col = 1;
+                    second[k] = false;
+                } else if (fr + 1 < f1[k]) {   // (mono_pair of celt_synth_kernel)
+                    const int fl = p.transient[fr * p.flag_stride + lone_col];
+                    second[k] = (fl >> 1) == 0 && p.transient[(fr + 1) * p.flag_stride + lone_col] == fl;
+                }
+            }
             const uint32_t base = smem_u32(gws);
-            if (st.shape == 3) group_store_frame_general(p, base + st.planes, st.q0, st.T, out, nsamples);
-            else group_store_frame(st, base, out, niter);
-            mbar_arrive(&gws->empty);   // (release: this thread's reads of the planes are done)
+            if (st.shape == 3) group_store_frame_general(p, base + st.planes, st.q0, st.T, out, nsamples, lone_slot, col);
+            else group_store_frame(st, base, out, niter, col);
+            __syncwarp();   // every lane's reads of the planes are done (their values have left in the stores)
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned *>(&gws->empty), 1u);
             nstored[k]++;
             if (++f[k] == f1[k]) {
                 item[k] = dynamic ? group_next_item(gws->claim, seq[k]) : item[k] + item_stride;
@@ -829,7 +877,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             mbar_init(&ws.bar, 1);
             if (kMode == kModeGroup && slot == 0) {
                 mbar_init(&ws.full, 32 * W);
-                mbar_init(&ws.empty, 32 * p.store_warps);
+                ws.empty = 0;
                 for (int i = 0; i < 4; i++) ws.claim[i] = 0;
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -859,7 +907,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
     long long item, item_stride, nitems;
     GroupLink grp;
     grp.full = &gws->full;
-    grp.empty = &gws->empty;
+    grp.stored = reinterpret_cast<volatile unsigned *>(&gws->empty);
+    grp.store_warps = (uint32_t)p.store_warps;
     grp.nstored = 0;
     grp.pending = false;
     uint32_t seq = 0;               // group mode: runs started so far
@@ -882,6 +931,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
     for (; item < nitems;) {
         long long run;
         int cb, nch, rows, flag_col, halo_bit, flag_col1 = -1;
+        bool lone = false;   // group mode: this warp carries a lone mono stream
         if (kMode == kModeGroup) {
             if (dynamic) {   // see group_next_item
                 seq++;
@@ -903,6 +953,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             // coefficient row -- its buffer stays zero -- and no reader.
             rows = sd.nch;
             nch = 2;
+            lone = NQ_LONE_PAIRS && p.lone_pairs && sd.nch == 1;   // ... unless two consecutive frames can share the warp (below)
             flag_col = sd.flag_col;
             halo_bit = sd.flag_col;
             if (kPaired && sd.flag_col1 != sd.flag_col) flag_col1 = sd.flag_col1;   // two mono streams in one warp
@@ -939,19 +990,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
         int tr1 = -1;
         if (kPaired && flag_col1 >= 0)
             tr1 = f < 0 ? (p.halo_transient >> flag_col1) & 1 : p.transient[f * p.flag_stride + flag_col1] & (kFlagTransient | kFlagReset);
-        // kModeMono: an item is one frame, or two consecutive 20 ms frames of the same block type
-        // (never the warm-up frame, whose output is not stored); nfr = frames of the current item
+        // kModeMono, and the warp of a LONE mono stream in group mode (a layout like 3.0 or 5.0: its
+        // second channel would be idle): an item is one frame, or two consecutive 20 ms frames of the
+        // same block type as the warp's two channels (never the warm-up frame, whose output is not
+        // stored); nfr = frames of the current item.  (Compile time except in group mode.)
+        const bool mono_like = kMode == kModeMono || (kMode == kModeGroup && lone);
+        const long long row2 = mono_like ? (long long)p.D * kFrame : kFrame;   // second row: next frame / other channel
         auto mono_pair = [&](long long g, int gflag) -> bool {
-            return kMode == kModeMono && g >= f0 && g + 1 < f1 && (gflag >> 1) == 0 && flags[(g + 1) * p.flag_stride] == gflag;
+            return mono_like && g >= f0 && g + 1 < f1 && (gflag >> 1) == 0 && flags[(g + 1) * p.flag_stride] == gflag;
         };
-        int nfr = (kMode == kModeMono && mono_pair(f, flag)) ? 2 : 1;
+        int nfr = (mono_like && mono_pair(f, flag)) ? 2 : 1;
         const int state_nch = rows;   // channels with a tail of their own (kModeMono: nch is reused as frames per item)
-        prefetch_rows(p, ws, lane, f, cb, kMode == kModeMono ? nfr : rows, true);   // (the previous run may have ended on a short frame)
+        prefetch_rows(p, ws, lane, f, cb, mono_like ? nfr : rows, true, row2);   // (the previous run may have ended on a short frame)
         while (f < f1) {
             if (kMode == kModeMono) nch = nfr;
+            const int lone_frames = (kMode == kModeGroup && lone) ? nfr : 0;
             const bool more = f + nfr < f1;
             const int next_flag = more ? flags[(f + nfr) * p.flag_stride] : 0;
-            const int next_nfr = (kMode == kModeMono && more && mono_pair(f + nfr, next_flag)) ? 2 : 1;
+            const int next_nfr = (mono_like && more && mono_pair(f + nfr, next_flag)) ? 2 : 1;
             int next_tr1 = -1;
             if (kPaired && flag_col1 >= 0 && more) next_tr1 = p.transient[(f + 1) * p.flag_stride + flag_col1] & (kFlagTransient | kFlagReset);
             // OPUS_RESET_STATE before this frame (celt_decoder_clean.c:846-859); two mono streams that share a
@@ -971,7 +1027,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             const int tr0 = flag & 1;
             const bool split = kPaired && tr1 >= 0 && tr1 != tr0;
             if (sh == 0) {
-                const int next_nch = kMode == kModeMono ? next_nfr : rows;
+                const int next_nch = mono_like ? next_nfr : rows;
                 // One pass -- or, for two mono streams in one warp that disagree about block switching,
                 // two: the short pass goes first and parks its channel's samples in that channel's own
                 // coefficient row; the long pass (which needs ws.x as its transpose buffer) leaves its
@@ -984,17 +1040,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                     stage1_common<kModeT>(tb, ws, lane, is_short, grp);
                     if (!is_short) {
                         // every lane has consumed its part of ws.in: the next item's rows can land while stage 2 runs
-                        if (more && !split) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, false);
-                        long_stage2<kModeT>(p, ws, lane, off, cb, nch, store, w4, vmask);
+                        if (more && !split) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, false, row2);
+                        long_stage2<kModeT>(p, ws, lane, off, cb, nch, store, w4, vmask, lone_frames);
                     } else if (kStereo && NQ_SHORT_ST != 2) {
                         // (samples leave from registers: ws.in is free as early as in a long frame)
                         if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, false);
                         short_stage2<kModeT>(p, tb, ws, lane, off, nch, store, vmask);
                     } else {
-                        short_stage2<kModeT>(p, tb, ws, lane, off, nch, store, vmask);
+                        short_stage2<kModeT>(p, tb, ws, lane, off, nch, store, vmask, lone_frames);
                         if (!split) {
                             short_output<kModeT>(p, ws, lane, off, cb, nch, store);
-                            if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, true);
+                            if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, true, row2);
                         }
                     }
                 }
@@ -1003,12 +1059,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
                     float *col = reinterpret_cast<float *>(ws.x) + cs;
                     for (int n = lane; n < kFrame; n += 32) col[2 * n] = ws.in[park_index<kMode>(cs, n)];
                     __syncwarp();
-                    if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, true);
+                    if (more) prefetch_rows(p, ws, lane, f + nfr, cb, next_nch, true, row2);
                 }
             } else {
                 if (kMode == kModeGroup) group_wait_plane_free(grp);
                 small_frame_planes(p.gen, p.gen->window, ws.in, ws.x, ws.tail, lane, kMode == kModeGroup ? rows : nch, sh, tr0 | ((tr1 >= 0 ? tr1 : tr0) << 1));
-                if (more) prefetch_rows(p, ws, lane, f + 1, cb, kMode == kModeMono ? next_nfr : rows, true);   // ws.in fully consumed
+                if (more) prefetch_rows(p, ws, lane, f + 1, cb, mono_like ? next_nfr : rows, true, row2);   // ws.in fully consumed
                 const int Nf = kFrame >> sh;
                 if (kMode != kModeGroup && store) {
                     const float *plane = reinterpret_cast<const float *>(ws.x);
@@ -1028,6 +1084,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) celt_synth_kernel(const __grid
             }
             if (kMode == kModeGroup && store) {
                 mbar_arrive(grp.full);   // this warp's plane of frame f is complete (release) ...
+                if (lone_frames == 2) {
+                    // ... and it holds frame f + 1 as well, in its second column: that frame's phase of `full`
+                    // opens when frame f's has completed (the other warps of the group have arrived for f)
+                    mbar_wait_long(grp.full, grp.nstored & 1, 64);
+                    grp.nstored++;
+                    mbar_arrive(grp.full);
+                }
                 grp.nstored++;
                 grp.pending = true;      // ... and stays intact until the store warps have arrived on `empty`
             }

@@ -89,6 +89,7 @@ struct SynthParams {
     int store_warps_cta;        // kModeGroup: store warps per CTA (group_store_warps_cta())
     int store_threads;          // kModeGroup: threads of a group's store warps in the store pass (group_store_threads())
     int store_shape;            // kModeGroup: loop shape of the store pass (0: 2 x LDS.64, 1: 4 x LDS.32, 2: with silent channels)
+    int lone_pairs;             // kModeGroup: the warp of a lone mono stream takes two consecutive frames as its two channels
     int halo_lm_shift;          // 3 - LM of the halo frame
     int halo_transient;         // flag(s) of the halo frame: bit s = stream s (bit 0 for everybody if !flag_per_stream)
     int flag_stride;            // bytes between the flag records of consecutive frames

@@ -159,6 +159,26 @@ def test_synth_batch_many_runs_vs_oracle(synth, C, p_tr):
     assert_parity(want_tail, tail, "tail")
 
 
+@pytest.mark.parametrize("C", [3, 5, 7])
+@pytest.mark.parametrize("pairs", ["0", "1"])
+def test_lone_mono_stream_frame_pairs(synth, monkeypatch, C, pairs):
+    """Layouts with an odd number of channels end on a lone mono stream; in the group kernel its warp
+    may take two consecutive frames of equal block type as its two channels (NQ_LONE_PAIRS forces the
+    choice either way; the default depends on the group size).  Both ways must give the oracle's
+    samples, and the SAME samples: the pairing only changes which warp lane computes what."""
+    rng = np.random.default_rng(4000 + C)
+    coef, tr = rand_batch(rng, 1200, C, 0.15)
+    tail_in = (rng.standard_normal((C, 60)) * 100).astype(np.float32)
+    want, want_tail, _ = port.synth_batch(coef, tr, tail_in, nthreads=8)
+    monkeypatch.setenv("NQ_LONE_PAIRS", pairs)
+    pcm, tail = synth.synth_batch(coef, tr, tail_in)
+    assert_parity(want, pcm, f"C {C} pairs {pairs}")
+    assert_parity(want_tail, tail, "tail")
+    monkeypatch.setenv("NQ_LONE_PAIRS", "1" if pairs == "0" else "0")
+    pcm2, tail2 = synth.synth_batch(coef, tr, tail_in)
+    assert np.array_equal(pcm, pcm2) and np.array_equal(tail, tail2)
+
+
 @pytest.mark.parametrize("C", [1, 2])
 def test_hybrid_start_band_17_and_narrow_end_bands(synth, C):
     """the CELT layer of a hybrid frame starts at band 17
