@@ -64,6 +64,35 @@ def run_ms(synth, frames, streams, coupled, p_tr, steps=5):
                 frac_of_6527=round(gbs / 6527.5, 3), sm_mhz=mhz)
 
 
+def run_lm(synth, frames, LM, p_tr, steps=5):
+    """Stereo frames of 2.5 / 5 / 10 ms (LM = 0 / 1 / 2) inside a batch: rows keep their 960-float stride, the
+    flag byte carries 3 - LM in bits 1-2, every frame names its first output sample (frame_offset)."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    N = 120 << LM
+    coef = torch.zeros((frames, 2, 960), dtype=torch.float32, device=dev)
+    coef[:, :, :N].uniform_(-1, 1, generator=g)
+    tr = ((torch.rand((frames, 1), generator=g, device=dev) < p_tr).to(torch.uint8) | ((3 - LM) << 1)).to(torch.uint8)
+    offs = (torch.arange(frames + 1, device=dev, dtype=torch.int64) * N)
+    pcm = torch.empty((frames * N, 2), dtype=torch.float32, device=dev)
+    call = lambda: synth.synth_batch_ms_torch(coef, tr, 1, 1, None, out=pcm, want_tail=False, frame_offset=offs)
+    for _ in range(2):
+        call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        call()
+    e1.record()
+    mhz = sm_clock()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    gbs = frames * 2 * N * 8 / (ms * 1e-3) / 1e9
+    return dict(frames=frames, LM=LM, frame_ms=2.5 * (1 << LM), p_transient=p_tr, ms=round(ms, 3), GBps_algorithmic=round(gbs, 1),
+                Mframes_per_s=round(frames / ms / 1e3, 2), frac_of_6527=round(gbs / 6527.5, 4), sm_mhz=mhz,
+                note="LM < 3 frames go through the compact warp routine small_frame_planes (correctness path)")
+
+
 if __name__ == "__main__":
     # --case frames,C,p_transient[,steps] (repeatable): run only these (used under ncu)
     cases = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--case=")]
@@ -75,10 +104,16 @@ if __name__ == "__main__":
         for c in ms_cases:   # --ms frames,streams,coupled,p_transient[,steps]
             fr, st, cp, p, *sx = c.split(",")
             print(json.dumps(run_ms(s, int(fr), int(st), int(cp), float(p), int(sx[0]) if sx else 5)), flush=True)
-        if cases or ms_cases:
+        lm_cases = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--lm=")]
+        for c in lm_cases:   # --lm frames,LM,p_transient[,steps]
+            fr, lm, p, *sx = c.split(",")
+            print(json.dumps(run_lm(s, int(fr), int(lm), float(p), int(sx[0]) if sx else 5)), flush=True)
+        if cases or ms_cases or lm_cases:
             sys.exit(0)
         for fr, st, cp in ((500_000, 5, 3), (600_000, 4, 2)):   # 7.1 / 5.1 multistream, own flags per stream
             print(json.dumps(run_ms(s, fr, st, cp, 0.028)), flush=True)
+        for fr, lm in ((200_000, 2), (200_000, 1), (200_000, 0)):   # 10 / 5 / 2.5 ms frames
+            print(json.dumps(run_lm(s, fr, lm, 0.028, 2)), flush=True)
         for frames, C, p in [(2_000_000, 2, 0.0), (2_000_000, 2, 0.028), (2_000_000, 2, 0.2), (2_000_000, 2, 1.0),
                              (4_000_000, 1, 0.028), (500_000, 8, 0.028), (500_000, 8, 0.2), (1_300_000, 3, 0.028), (700_000, 6, 0.028), (1_000_000, 4, 0.028),
                              (20_000, 2, 0.028), (2_000, 2, 0.028)]:

@@ -51,7 +51,7 @@ def main():
             long_form(p, os.path.join(DST, b.replace(".raw.csv", ".csv")))
         elif b.endswith("_launches_bench.csv"):
             launches(p, os.path.join(DST, b))
-        elif b.endswith(".json") or b.endswith(".jsonl"):
+        elif b.endswith(".json") or b.endswith(".jsonl") or (b.endswith(".txt") and "_src_" in b):
             shutil.copy(p, os.path.join(DST, b))
         else:
             continue
