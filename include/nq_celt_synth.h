@@ -369,6 +369,10 @@ NQ_API void printCudaVersion(void);
  * NQ_BAD_ARG exactly where the batch entries return them. */
 NQ_API int nq_celt_debug_plan(int channels, int streams, int coupled_streams, const unsigned char *mapping,
                               int64_t nframes, int num_sms, int64_t out[12]);
+/* The runs a batch of `nframes` frames is cut into (pure host code): run_first[r] = first frame of run r
+ * for r < *nruns, run_first[*nruns] = nframes (as far as `capacity` entries allow). */
+NQ_API int nq_celt_debug_runs(int channels, int64_t nframes, int num_sms, int64_t *run_first, int64_t capacity,
+                              int64_t *nruns);
 /* Copies the host-built tables: t_long [16*31*2], t_short [2*30*2],
  * window [120], trig [481] (any pointer may be NULL). */
 NQ_API void nq_celt_debug_tables(float *t_long, float *t_short, float *window, float *trig);

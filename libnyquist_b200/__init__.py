@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     "nq_celt_sink_flush_pinned", "nq_celt_sink_flush_many", "nq_celt_sink_begin_upload", "nq_celt_sink_trim_pool", "nq_celt_ctx_device", "nq_celt_ctx_stream", "nq_celt_sink_attach", "nq_celt_sink_finish",
     "nq_clt_mdct_backward", "nq_clt_mdct_backward_B1_C2", "nq_celt_mdct_backward_host",
     "nq_compute_inv_mdcts", "nq_opus_ifft_host", "processMDCTCuda", "processMDCTCudaB1C2", "cleanupCudaBuffers",
-    "printCudaVersion", "nq_celt_debug_tables", "nq_celt_debug_plan",
+    "printCudaVersion", "nq_celt_debug_tables", "nq_celt_debug_plan", "nq_celt_debug_runs",
 ]
 
 
@@ -162,6 +162,21 @@ def debug_plan(channels, streams=0, coupled_streams=0, mapping=None, nframes=1_0
     if rc != NQ_OK:
         raise NqError(rc, "nq_celt_debug_plan")
     return dict(zip(PLAN_FIELDS, [int(v) for v in out]))
+
+
+def debug_runs(channels, nframes, num_sms=148):
+    """First frame of every run a batch is cut into, plus nframes at the end (pure host code)."""
+    L = load_library()
+    L.nq_celt_debug_runs.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    n = C.c_int64(0)
+    rc = L.nq_celt_debug_runs(int(channels), int(nframes), int(num_sms), None, 0, C.byref(n))
+    if rc != NQ_OK:
+        raise NqError(rc, "nq_celt_debug_runs")
+    first = np.zeros(n.value + 1, np.int64)
+    rc = L.nq_celt_debug_runs(int(channels), int(nframes), int(num_sms), _vp(first), first.size, C.byref(n))
+    if rc != NQ_OK:
+        raise NqError(rc, "nq_celt_debug_runs")
+    return first
 
 
 # ---- reference-shaped single calls (host buffers, synchronous) ------------

@@ -466,6 +466,24 @@ int nq_celt_debug_plan(int channels, int streams, int coupled_streams, const uns
     return NQ_OK;
 }
 
+int nq_celt_debug_runs(int channels, int64_t nframes, int num_sms, int64_t *run_first, int64_t capacity, int64_t *nruns)
+{
+    if (channels < 1 || channels > 255 || nframes < 0 || num_sms < 1 || !nruns) return NQ_BAD_ARG;
+    SynthParams p;
+    memset(&p, 0, sizeof p);
+    p.nframes = nframes;
+    int mode = 0;
+    const int rc = plan_layout(plain_layout(channels), num_sms, nframes, &p, &mode);
+    if (rc != NQ_OK) return rc;
+    *nruns = p.nruns;
+    for (long long r = 0; r <= p.nruns && run_first && r < capacity; r++) {
+        long long f0 = nframes, f1 = nframes;
+        if (r < p.nruns) run_range(p, r, &f0, &f1);
+        run_first[r] = f0;
+    }
+    return NQ_OK;
+}
+
 void nq_celt_debug_tables(float *t_long, float *t_short, float *window, float *trig)
 {
     const HostTables &t = host_tables();

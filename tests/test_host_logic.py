@@ -148,6 +148,25 @@ def test_plan_plain_layouts():
     assert small["frames_per_run"] == 8 and small["runs"] == 13
 
 
+@pytest.mark.parametrize("C", [1, 2, 3, 8])
+def test_runs_tile_the_batch(C):
+    """Every frame belongs to exactly one run, runs are in order, none is empty; a dynamically claimed
+    launch ends on quarter-length runs (the last half wave's worth of frames)."""
+    for nframes in (1, 7, 8, 9, 100, 2071, 2072 * 8, 2072 * 8 + 1, 123_457, 397_823, 397_824, 1_000_000, 1_250_000, 10_000_000):
+        first = nq.debug_runs(C, nframes)
+        assert first[0] == 0 and first[-1] == nframes
+        lens = np.diff(first)
+        assert (lens > 0).all(), (C, nframes)
+        big = int(lens[0])
+        assert lens.max() == big
+        if len(lens) > 1:
+            assert (lens[:-1] == big).all() or set(lens[:-1].tolist()) <= {big, big // 4}
+            small = np.flatnonzero(lens[:-1] != big)
+            if small.size:   # the small runs are the tail of the list, and there is about half a wave of frames in them
+                assert small[0] + small.size == len(lens) - 1 or (lens[small[0]:] <= big // 4).all()
+                assert (lens[small[0]:] <= big // 4).all()
+
+
 def test_plan_multistream_layouts():
     s71 = nq.debug_plan(8, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7])
     # 3 coupled streams + the 2 mono streams sharing one warp = 4 synthesis warps, 3 groups (+ 3 store warps) per CTA
