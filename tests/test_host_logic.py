@@ -236,3 +236,40 @@ def test_overlay_files_contain_no_reference_code():
         for l in joined:
             assert l.startswith("#") or l.startswith("void nqref_tap") or l.startswith("int ") or l.startswith("const float") or l.endswith(";"), (rel, l)
         assert len(joined) < 45, rel   # (preprocessor lines only, see the loop above)
+
+
+# ---- frame sink: argument checking is host code (no device needed) ------------------------------
+def test_sink_push_validation_without_a_device():
+    import ctypes as C
+    L = nq.load_library()
+    L.nq_celt_sink_push_at.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+    sink = nq.FrameSink(2, 1, 1, [0, 1])
+    freq = np.zeros((2, 960), np.float32)
+    post = np.zeros(1, nq.POST_FRAME_DTYPE)
+    post["N"] = 960
+    # (a valid push page-locks a block of host memory, which needs the CUDA driver: the GPU tests do that)
+    with pytest.raises(nq.NqError):                      # stream index
+        sink.push(1, freq, 0, post[0])
+    with pytest.raises(nq.NqError):                      # a coupled stream pushes two channels
+        sink.push(0, freq[:1], 0, post[0])
+    with pytest.raises(nq.NqError):                      # shortBlocks must be 0 or 1 << LM
+        sink.push(0, freq, 4, post[0])
+    bad = post.copy()
+    bad["N"] = 480
+    with pytest.raises(nq.NqError):                      # post->N must say the frame size
+        sink.push(0, freq, 0, bad[0])
+    # a frame with a place of its own (files that switch coding modes) needs streaming mode
+    rc = L.nq_celt_sink_push_at(sink._h, 0, freq.ctypes.data, 2, 960, 0, post.ctypes.data, 4800)
+    assert rc != nq.NQ_OK and b"streaming" in L.nq_celt_sink_last_error(sink._h)
+    assert L.nq_celt_sink_side_count(sink._h) == 0
+    assert sink.pending_frames == 0
+    sink.reset()
+    L.nq_celt_sink_reset_stream.argtypes = [C.c_void_p, C.c_int]
+    L.nq_celt_sink_reset_stream(sink._h, 0)
+    L.nq_celt_sink_reset_stream(sink._h, 7)              # out of range: ignored
+    sink.close()
+    # multistream sinks take no frames with a place of their own at all
+    ms = nq.FrameSink(8, 5, 3, [0, 6, 1, 2, 3, 4, 5, 7])
+    rc = L.nq_celt_sink_push_at(ms._h, 0, freq.ctypes.data, 2, 960, 0, post.ctypes.data, 0)
+    assert rc != nq.NQ_OK and b"single-stream" in L.nq_celt_sink_last_error(ms._h)
+    ms.close()
