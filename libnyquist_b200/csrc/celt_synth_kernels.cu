@@ -513,8 +513,10 @@ __device__ __forceinline__ void long_stage2(const SynthParams &p, WarpSmem &ws, 
 // 59 - m), 16 contiguous bytes per lane pair (h = 0, 1) -- so the consumed coefficient rows are free
 // for the next frame's TMA copy as early as in a long frame.  The other modes park the finished
 // samples in the channel's own -- consumed -- coefficient row, ws.in[c][0..960), for short_output.
-// The raw tail of sub-block 7 replaces the old one in ws.tail; the old entries a group of five
-// trips needs are read before the group's first write (one warp barrier per group).
+// The raw tail of sub-block 7 replaces the old one in ws.tail; the old entries a group of 15
+// trips needs are read before the group's first write (one warp barrier per group; groups of 5:
+// all-transient 0.825 of the HBM peak, 15: 0.835, all 30 unrolled: the code outgrows the
+// instruction cache, 0.89 instead of 0.97 on the 2.8 % mix).
 template <int kModeT>
 __device__ __forceinline__ void short_stage2(const SynthParams &p, const FastTables &tb, WarpSmem &ws, int lane, long long off, int nch,
                                              bool store, int vmask, int lone = 0)
@@ -549,7 +551,10 @@ __device__ __forceinline__ void short_stage2(const SynthParams &p, const FastTab
         gdst = reinterpret_cast<float2 *>(p.pcm + off * 2) + 120 * b + (c ? 59 - h : 60 + h);
         gstep = c ? -2 : 2;
     }
-    constexpr int kGroup = 5;
+#ifndef NQ_SHORT_GROUP
+#define NQ_SHORT_GROUP 15
+#endif
+    constexpr int kGroup = NQ_SHORT_GROUP;   // trips per warp barrier (divides 30)
 #pragma unroll 1
     for (int i0 = 0; i0 < 30; i0 += kGroup) {
         float told[kGroup];
