@@ -74,13 +74,21 @@ def ncu_traffic_bytes_per_frame():
 
 # Only the JSON line may reach stdout: NCCL (and anything else that writes to the C-level stdout,
 # e.g. "NCCL version ..." at communicator creation) is sent to stderr for the whole run.
-_REAL_STDOUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+# (Done by main() / the probes that import this module, not at import time: tests import it too.)
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(line):
-    _REAL_STDOUT.write(json.dumps(line) + "\n")
-    _REAL_STDOUT.flush()
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def workload_name(frames):
@@ -506,6 +514,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational other-shapes / file-decode legs")
     args = ap.parse_args()
+    protect_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)

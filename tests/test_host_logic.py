@@ -273,3 +273,29 @@ def test_sink_push_validation_without_a_device():
     rc = L.nq_celt_sink_push_at(ms._h, 0, freq.ctypes.data, 2, 960, 0, post.ctypes.data, 0)
     assert rc != nq.NQ_OK and b"single-stream" in L.nq_celt_sink_last_error(ms._h)
     ms.close()
+
+
+# ---- bench.py's own checker must be able to fail ------------------------------------------------
+def test_bench_spot_check_detects_a_wrong_frame():
+    """bench.py compares three frames of every rank's timed output with the oracle (first frame after
+    the halo, one in the middle, the last but one).  Fed the oracle's own output it reports ~0; with
+    one of those frames damaged, or with the halo ignored, it reports the damage."""
+    import torch
+    import bench
+    from oracle import port
+    rng = np.random.default_rng(12)
+    n = 40
+    coef = (rng.standard_normal((n + 1, 2, 960)) * 300).astype(np.float32)
+    tr = (rng.uniform(size=n + 1) < 0.2).astype(np.uint8)
+    tr[0] = 0                                            # the halo frame is a long block (halo_transient=0 in bench.py)
+    full, _, _ = port.synth_batch(coef, tr, None)        # frame 0 is the halo of the "rank"
+    pcm = torch.from_numpy(full[960:].copy())
+    c, t, halo = torch.from_numpy(coef[1:]), torch.from_numpy(tr[1:]), torch.from_numpy(coef[0])
+    assert bench.oracle_spot_check(np, c, t, pcm, halo, n) <= 1e-7
+    no_halo, _, _ = port.synth_batch(coef[1:], tr[1:], None)
+    assert bench.oracle_spot_check(np, c, t, torch.from_numpy(no_halo), None, n) <= 1e-7
+    assert bench.oracle_spot_check(np, c, t, torch.from_numpy(no_halo), halo, n) > 1e-4   # first frame lacks the halo's tail
+    for f in (0, n // 3, n - 2):
+        bad = pcm.clone()
+        bad[f * 960 + 17, 1] += 40.0
+        assert bench.oracle_spot_check(np, c, t, bad, halo, n) > 1e-3

@@ -16,7 +16,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench                      # noqa: E402  (near_gpu, emit; sends the C-level stdout to stderr)
+import bench                      # noqa: E402  (near_gpu, emit, protect_stdout)
 import numpy as np                # noqa: E402
 import torch                      # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -33,6 +33,7 @@ def sh(cmd):
 
 
 def main():
+    bench.protect_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
