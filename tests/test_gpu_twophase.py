@@ -252,6 +252,39 @@ def test_mode_switching_file_matches_the_reference(twophase, tmp_path, a, b, cha
     assert float(np.abs(want).max()) > 0.1
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_random_mode_schedules_match_or_are_refused(twophase, tmp_path, seed):
+    """Random walks through the coding modes (random switch points, mono / stereo, bitrates from 12 to
+    64 kbit/s, some switches only a frame apart): the loader either returns the reference decoder's PCM
+    or refuses the file loudly (switches the encoder makes without a redundancy frame need loss
+    concealment, which the bundled decoder does not define) -- never anything else."""
+    if not ref.available():
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    rng = np.random.default_rng(900 + seed)
+    channels = int(rng.integers(1, 3))
+    nfr = int(rng.integers(40, 90))
+    modes = list(MODES.values())
+    first = int(rng.choice(modes))
+    sched, f, cur = [], 0, first
+    while True:
+        f += int(rng.choice([1, 2, 3, 7, 15, 25]))
+        if f >= nfr - 1:
+            break
+        cur = int(rng.choice([m for m in modes if m != cur]))
+        sched.append((f, cur))
+    bitrate = int(rng.choice([12000, 20000, 32000, 48000, 64000]))
+    data = ref.encode_mode_schedule(_switch_signal(960 * nfr, channels, seed), first, sched, bitrate)
+    path = tmp_path / "walk.opus"
+    path.write_bytes(data)
+    want, recs = ref.decode_bytes(data, record=True)
+    got, ch, sr, tm, wall = load(twophase, str(path))
+    if got is None:
+        return                       # refused (the message names the reason); the reference alone decodes it
+    assert ch == channels and got.shape == want.shape
+    err = float(np.abs(got.astype(np.float64) - want).max())
+    assert err <= 1e-5 and snr_db(want, got) >= 100.0, (seed, first, sched, bitrate, err)
+
+
 def test_mode_walk_fixture_matches_the_reference(twophase):
     """tests/golden/modeswitch.opus (make_golden.py): CELT -> hybrid -> SILK -> hybrid -> CELT -> SILK ->
     CELT -> hybrid in one file: 7 redundancy frames, 1 fade-out frame, 110 ordinary CELT frames."""
