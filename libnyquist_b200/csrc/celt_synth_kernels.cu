@@ -198,7 +198,12 @@ __device__ __forceinline__ void group_wait_plane_free(GroupLink &g)
 {
     if (g.pending) {
         const unsigned need = g.nstored * g.store_warps;
-        while ((int)(*g.stored - need) < 0) {}
+#ifndef NQ_PLANE_WAIT_NS
+#define NQ_PLANE_WAIT_NS 50
+#endif
+        while ((int)(*g.stored - need) < 0) {
+            if (NQ_PLANE_WAIT_NS > 0) __nanosleep(NQ_PLANE_WAIT_NS);   // leave the issue slots to the warps that have work
+        }
         g.pending = false;
     }
 }
